@@ -1,0 +1,186 @@
+// K2 -- neighbour search on the sorted particles.
+//
+// Replaces Particles::gridNNS (/root/reference/demonstrator/src/Particles.cpp:324-365),
+// Domain::getNeighborCells (Domain.cpp:83-118), Particles::createGhostParticles (:2113-2191) and the
+// brute-force Particles::ghostNNS (:2237-2260).
+//
+// One thread per particle walks the 3^D stencil in the reference's order (x outer, y, z inner);
+// a stencil cell is a contiguous range of the sorted arrays, so candidates are read with unit
+// stride and lanes of the same cell broadcast.  The cutoff test is the reference's expression,
+// evaluated without FMA contraction (dist_sqr_exact), so the neighbour SETS are bit-exact.
+//
+// Periodic images are not materialised as ghost particles: a stencil cell that wraps around the box
+// yields candidates whose image position is computed on the fly with the reference's formulas
+// (image_coord) and whose existence test is the reference's threshold (image_exists).  Because
+// cellSize >= h (Domain.cpp:10-22) every ghost within h of a particle lives in a wrapped stencil
+// cell, so the result equals the brute-force search over all ghosts.  Ghost entries are appended
+// after the regular ones and ordered by parent original index (== ascending ghost index).
+#include "mlh_internal.cuh"
+
+namespace {
+
+template <int D>
+struct StencilCell {
+    int cell; // local cell id or -1
+    int code; // image code (2 bits per dim), 0 = not wrapped
+};
+
+// neighbour cell (cx+ox, cy+oy, cz+oz) of the local grid with periodic wrap information
+template <int D, bool PER>
+__device__ __forceinline__ StencilCell<D> stencil_cell(const Grid &g, const int *ci, const int *off) {
+    StencilCell<D> r;
+    r.code = 0;
+    int n[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        int v = ci[k] + off[k];
+        if (g.sliced && k == g.slab_dim) {
+            // local layers: index is always inside the local grid for owned cells; the wrap is
+            // decided by the GLOBAL layer
+            int gl = g.layer0 + v;
+            if (v < 0 || v >= g.lcells[k]) { r.cell = -1; return r; }
+            if (gl < 0) {
+                if (!PER) { r.cell = -1; return r; }
+                r.code |= 2 << (2 * k);
+            } else if (gl >= g.cells[k]) {
+                if (!PER) { r.cell = -1; return r; }
+                r.code |= 1 << (2 * k);
+            }
+        } else {
+            if (v < 0) {
+                if (!PER) { r.cell = -1; return r; }
+                v = g.cells[k] - 1;
+                r.code |= 2 << (2 * k); // parents near the high side, image below min
+            } else if (v >= g.cells[k]) {
+                if (!PER) { r.cell = -1; return r; }
+                v = 0;
+                r.code |= 1 << (2 * k); // parents near the low side, image above max
+            }
+        }
+        n[k] = v;
+    }
+    r.cell = n[0] + g.lcells[0] * (n[1] + g.lcells[1] * n[2]);
+    return r;
+}
+
+template <int D, bool PER>
+__global__ void __launch_bounds__(128) k_neighbours(const Params p) {
+    int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.own_end) return;
+    const Grid &g = p.grid;
+    double xi[3];
+#pragma unroll
+    for (int k = 0; k < D; ++k) xi[k] = p.d.x[k][i];
+    int c = p.d.cell[i];
+    int ci[3];
+    ci[0] = c % g.lcells[0];
+    ci[1] = (c / g.lcells[0]) % g.lcells[1];
+    ci[2] = D == 3 ? c / (g.lcells[0] * g.lcells[1]) : 0;
+
+    int cnt = 0;
+    bool overflow = false;
+    // ---- pass A: regular neighbours, Particles.cpp:335-359 ----
+    int off[3] = {0, 0, 0};
+    for (off[0] = -1; off[0] <= 1; ++off[0])
+        for (off[1] = -1; off[1] <= 1; ++off[1])
+            for (off[2] = (D == 3 ? -1 : 0); off[2] <= (D == 3 ? 1 : 0); ++off[2]) {
+                StencilCell<D> sc = stencil_cell<D, PER>(g, ci, off);
+                if (sc.cell < 0 || sc.code != 0) continue;
+                int s = p.d.cell_start[sc.cell], e = p.d.cell_start[sc.cell + 1];
+                for (int j = s; j < e; ++j) {
+                    if (j == i) continue;
+                    double d[3];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) d[k] = __dsub_rn(p.d.x[k][j], xi[k]);
+                    if (dist_sqr_exact<D>(d) < p.hSqr) {
+                        if (cnt < p.max_ni)
+                            p.d.nnl[(size_t)cnt * p.ncap + i] = j;
+                        else
+                            overflow = true;
+                        ++cnt;
+                    }
+                }
+            }
+    int nreg = cnt < p.max_ni ? cnt : p.max_ni;
+    p.d.noi[i] = nreg;
+    int ng = 0;
+    if (PER) {
+        // ---- pass B: periodic images, Particles.cpp:2113-2191 + :2237-2260 ----
+        for (off[0] = -1; off[0] <= 1; ++off[0])
+            for (off[1] = -1; off[1] <= 1; ++off[1])
+                for (off[2] = (D == 3 ? -1 : 0); off[2] <= (D == 3 ? 1 : 0); ++off[2]) {
+                    StencilCell<D> sc = stencil_cell<D, PER>(g, ci, off);
+                    if (sc.cell < 0 || sc.code == 0) continue;
+                    int rcode = reverse_code(sc.code);
+                    int s = p.d.cell_start[sc.cell], e = p.d.cell_start[sc.cell + 1];
+                    for (int j = s; j < e; ++j) {
+                        double d[3];
+                        bool exists = true;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            int ck = (sc.code >> (2 * k)) & 3;
+                            double xj = p.d.x[k][j];
+                            exists = exists && image_exists(xj, ck, g.bmin[k], g.bmax[k], p.h);
+                            d[k] = __dsub_rn(image_coord(xj, ck, g.bmin[k], g.bmax[k]), xi[k]);
+                        }
+                        bool hit = exists && (dist_sqr_exact<D>(d) < p.hSqr);
+                        if (!hit && p.symmetric_seam) {
+                            // the pair as particle j sees it (image of i with the opposite code)
+                            bool ex2 = true;
+                            double d2[3];
+#pragma unroll
+                            for (int k = 0; k < D; ++k) {
+                                int ck = (rcode >> (2 * k)) & 3;
+                                ex2 = ex2 && image_exists(xi[k], ck, g.bmin[k], g.bmax[k], p.h);
+                                d2[k] = __dsub_rn(image_coord(xi[k], ck, g.bmin[k], g.bmax[k]), p.d.x[k][j]);
+                            }
+                            hit = ex2 && (dist_sqr_exact<D>(d2) < p.hSqr);
+                        }
+                        if (hit) {
+                            if (cnt < p.max_ni)
+                                p.d.nnl[(size_t)cnt * p.ncap + i] = j | (sc.code << MLH_NNL_IDX_BITS);
+                            else
+                                overflow = true;
+                            ++cnt;
+                        }
+                    }
+                }
+        int ntot = cnt < p.max_ni ? cnt : p.max_ni;
+        ng = ntot - nreg;
+        // order ghost entries by parent original index (ghostNNS scans ghosts in creation order,
+        // which is ascending parent index, Particles.cpp:2116,2241)
+        for (int a = nreg + 1; a < ntot; ++a) {
+            int ea = p.d.nnl[(size_t)a * p.ncap + i];
+            int ka = p.d.id[ea & MLH_NNL_IDX_MASK];
+            int b = a - 1;
+            while (b >= nreg) {
+                int eb = p.d.nnl[(size_t)b * p.ncap + i];
+                if (p.d.id[eb & MLH_NNL_IDX_MASK] <= ka) break;
+                p.d.nnl[(size_t)(b + 1) * p.ncap + i] = eb;
+                --b;
+            }
+            p.d.nnl[(size_t)(b + 1) * p.ncap + i] = ea;
+        }
+    }
+    p.d.noig[i] = ng;
+    if (overflow) atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
+}
+
+} // namespace
+
+int mlh_launch_neighbours(mlh_ctx *c) {
+    Params &p = c->p;
+    int n = p.own_end - p.own_begin;
+    mlh_prof_begin(c, KID_NEIGHBOURS);
+    if (p.D == 2 && p.periodic)
+        k_neighbours<2, true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+    else if (p.D == 2)
+        k_neighbours<2, false><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+    else if (p.periodic)
+        k_neighbours<3, true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+    else
+        k_neighbours<3, false><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+    mlh_prof_end(c, KID_NEIGHBOURS);
+    MLH_CUDA_CHECK(c, cudaGetLastError());
+    return MLH_OK;
+}

@@ -1,0 +1,193 @@
+// K3b -- locally-centred least-squares gradients, slope limiter and the CFL time step.
+//
+// Replaces (per particle, reference operation order kept):
+//   psi-tilde weights of compPsijTilde  /root/reference/demonstrator/src/Particles.cpp:1230-1252 (ghosts :2400-2453)
+//   Particles::gradient for rho, vx, vy, (vz), P   :1257-1270 (ghosts :2457-2502)
+//   Particles::slopeLimiter             :1313-1444 (quirks Q1 abs, Q2 DBL_MIN "max", Q6 alpha rule)
+//   Particles::compGlobalTimestep       :1446-1485 (quirk Q7: regular neighbours only) -- the global
+//                                       min is a warp-shuffle + one atomicMin per block on the
+//                                       ordered bit pattern of the (positive) double.
+// The limiter reads only neighbours' VALUES (not their gradients), so gradient + limiter fuse into
+// one kernel with two sweeps over the particle's list; ghost values are the parents' values
+// (updateGhostState/updateGhostGradients, :2193-2222, need no copy here).
+// Roofline: 18 (2D) / 30 (3D) algorithmic doubles per particle, ~100 FP64 ops per neighbour -> FP64-bound.
+#include "mlh_internal.cuh"
+#include <cfloat>
+
+namespace {
+
+template <int D>
+__device__ __forceinline__ double dot_seq(const double *a, const double *b) { // Helper::dotProduct, Helper.cpp:20-26
+    double res = 0.;
+#pragma unroll
+    for (int k = 0; k < D; ++k) res = __dadd_rn(res, __dmul_rn(a[k], b[k]));
+    return res;
+}
+
+template <int D, bool PER>
+__global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
+    constexpr int NF = D + 2;
+    int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    double dt_i = DBL_MAX;
+    if (i < p.own_end) {
+        // field tables: rho, vx, vy, (vz), P  (order of MeshlessScheme.cpp:114-120 and Particles.cpp:1329-1335)
+        const double *fld[NF];
+        int fslot[NF];
+        fld[0] = p.d.rho; fslot[0] = 0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { fld[1 + k] = p.d.v[k]; fslot[1 + k] = 1 + k; }
+        fld[NF - 1] = p.d.P; fslot[NF - 1] = 4;
+
+        double xi[3], fi[NF], B[D * D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) xi[k] = p.d.x[k][i];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) fi[f] = fld[f][i];
+#pragma unroll
+        for (int k = 0; k < D * D; ++k) B[k] = p.d.B[k][i];
+        const double omg = p.d.omega[i];
+        const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
+
+        double g[NF][D];
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int a = 0; a < D; ++a) g[f][a] = 0.;
+
+        // ---- sweep 1: gradients ----
+        for (int s = 0; s < ntot; ++s) {
+            const int e = p.d.nnl[(size_t)s * p.ncap + i];
+            const int j = e & MLH_NNL_IDX_MASK;
+            double d[3], r;
+            neighbour_geometry<D, PER>(p, xi, e, d, &r);
+            const double psij = __ddiv_rn(cubic_spline(r, p), omg);
+            double pt[D];
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                double acc = 0.;
+#pragma unroll
+                for (int b = 0; b < D; ++b) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(B[D * a + b], d[b]), psij));
+                pt[a] = acc;
+            }
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const double df = __dsub_rn(fld[f][j], fi[f]);
+#pragma unroll
+                for (int a = 0; a < D; ++a) g[f][a] = __dadd_rn(g[f][a], __dmul_rn(df, pt[a]));
+            }
+        }
+        if (p.debug_capture) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                for (int a = 0; a < D; ++a) p.d.gpre[fslot[f] * 3 + a][i] = g[f][a];
+        }
+
+        // ---- sweep 2: slope limiter extrema + signal velocity ----
+        if (p.slope_limiting) {
+            double maxNgb[NF], minNgb[NF], maxMid[NF], minMid[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                maxNgb[f] = DBL_MIN; // quirk Q2: smallest positive normal, not -inf
+                minNgb[f] = DBL_MAX;
+                maxMid[f] = DBL_MIN;
+                minMid[f] = DBL_MAX;
+            }
+            for (int s = 0; s < ntot; ++s) {
+                const int e = p.d.nnl[(size_t)s * p.ncap + i];
+                const int j = e & MLH_NNL_IDX_MASK;
+                double xijxi[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    double xj = p.d.x[k][j];
+                    if (PER) xj = image_coord(xj, (e >> (MLH_NNL_IDX_BITS + 2 * k)) & 3, p.grid.bmin[k], p.grid.bmax[k]);
+                    const double xij = __ddiv_rn(__dadd_rn(xi[k], xj), 2.); // FIRST_ORDER_QUAD_POINT, :1355-1356
+                    xijxi[k] = __dsub_rn(xij, xi[k]);
+                }
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const double fj = fld[f][j];
+                    if (maxNgb[f] < fj) maxNgb[f] = fj;
+                    if (minNgb[f] > fj) minNgb[f] = fj;
+                    const double fij = __dadd_rn(fi[f], dot_seq<D>(g[f], xijxi));
+                    if (maxMid[f] < fij) maxMid[f] = fij;
+                    if (minMid[f] > fij) minMid[f] = fij;
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const double alphaMax = q1_abs(__ddiv_rn(__dsub_rn(maxNgb[f], fi[f]), __dsub_rn(maxMid[f], fi[f])), p.abs_mode);
+                const double alphaMin = q1_abs(__ddiv_rn(__dsub_rn(fi[f], minNgb[f]), __dsub_rn(fi[f], minMid[f])), p.abs_mode);
+                if (alphaMin <= alphaMax && __dmul_rn(p.beta, alphaMin) < 1.) {
+#pragma unroll
+                    for (int a = 0; a < D; ++a) g[f][a] = __dmul_rn(g[f][a], alphaMin);
+                } else if (alphaMax <= alphaMin && __dmul_rn(p.beta, alphaMax) < 1.) {
+#pragma unroll
+                    for (int a = 0; a < D; ++a) g[f][a] = __dmul_rn(g[f][a], alphaMax);
+                }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int a = 0; a < D; ++a) p.d.g[fslot[f] * 3 + a][i] = g[f][a];
+
+        // ---- CFL: regular neighbours only (quirk Q7), vSig starts at DBL_MIN (quirk Q2) ----
+        double vSig = DBL_MIN;
+        const double ci = p.d.cs[i];
+        double vi[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) vi[k] = p.d.v[k][i];
+        for (int s = 0; s < nreg; ++s) {
+            const int j = p.d.nnl[(size_t)s * p.ncap + i];
+            const double cj = p.d.cs[j];
+            double xij[D], vij[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                xij[k] = __dsub_rn(xi[k], p.d.x[k][j]);
+                vij[k] = __dsub_rn(vi[k], p.d.v[k][j]);
+            }
+            double vijxij = __ddiv_rn(dot_seq<D>(vij, xij), sqrt(dot_seq<D>(xij, xij)));
+            vijxij = vijxij < 0. ? vijxij : 0.;
+            const double vSig_i = __dsub_rn(__dadd_rn(ci, cj), vijxij);
+            vSig = vSig_i > vSig ? vSig_i : vSig;
+        }
+        dt_i = __ddiv_rn(__dmul_rn(p.cfl, p.h), vSig);
+        if (!(dt_i < DBL_MAX)) dt_i = DBL_MAX; // `dt < dt_` never selects NaN / inf
+    }
+    // ---- block min -> global atomicMin (positive doubles order like their bit patterns) ----
+    unsigned long long bits = (unsigned long long)__double_as_longlong(dt_i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+        bits = other < bits ? other : bits;
+    }
+    __shared__ unsigned long long wmin[4];
+    if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long b = wmin[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) b = wmin[w] < b ? wmin[w] : b;
+        atomicMin(p.d.dt_bits, b);
+    }
+}
+
+} // namespace
+
+int mlh_launch_gradient(mlh_ctx *c) {
+    Params &p = c->p;
+    int n = p.own_end - p.own_begin;
+    // the dt accumulator was set to DBL_MAX (Particles.cpp:1447) by k_density_matrix
+    mlh_prof_begin(c, KID_GRADIENT);
+    if (p.D == 2 && p.periodic)
+        k_gradient_limit<2, true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+    else if (p.D == 2)
+        k_gradient_limit<2, false><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+    else if (p.periodic)
+        k_gradient_limit<3, true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+    else
+        k_gradient_limit<3, false><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+    mlh_prof_end(c, KID_GRADIENT);
+    MLH_CUDA_CHECK(c, cudaGetLastError());
+    return MLH_OK;
+}

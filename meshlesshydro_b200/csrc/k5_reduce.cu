@@ -1,0 +1,196 @@
+// K0 / K5 helpers -- bounding box (non-periodic grid rebuild), conservation sums, un-permutation.
+//
+//   Particles::getDomainLimits   /root/reference/demonstrator/src/Particles.cpp:228-267  (quirks Q2, Q8)
+//   Particles::sumVolume/sumMass/sumEnergy/sumMomentumX/Y/Z   :2830-2886
+// All HBM-bound streaming reductions (warp shuffle -> block -> one atomic per block).
+#include "mlh_internal.cuh"
+#include <cfloat>
+
+namespace {
+
+__device__ __forceinline__ void atomic_min_double(double *addr, double v) {
+    // total order trick valid for all finite doubles
+    unsigned long long *a = (unsigned long long *)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (!(v < __longlong_as_double((long long)assumed))) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_max_double(double *addr, double v) {
+    unsigned long long *a = (unsigned long long *)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (!(v > __longlong_as_double((long long)assumed))) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+
+__global__ void k_bbox_init(const Params p) {
+    int k = threadIdx.x;
+    if (k < 3) {
+        p.d.bbox[k] = DBL_MAX;      // running minimum starts at numeric_limits::max()  (:230)
+        p.d.bbox[3 + k] = DBL_MIN;  // running maximum starts at numeric_limits::min()  (:231, quirk Q2)
+    }
+}
+
+// min over all i, max over i >= 1 (x[0] always lowers the minimum first and is never tested
+// against the maximum: `if (x<min) .. else if (x>max)`, :240-244, quirk Q8)
+template <int D>
+__global__ void __launch_bounds__(256) k_bbox(const Params p) {
+    double mn[D], mx[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        mn[k] = DBL_MAX;
+        mx[k] = DBL_MIN;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.ncur; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double x = p.d.cx[k][i];
+            mn[k] = x < mn[k] ? x : mn[k];
+            if (i >= 1) mx[k] = x > mx[k] ? x : mx[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double a = __shfl_xor_sync(0xffffffffu, mn[k], o);
+            double b = __shfl_xor_sync(0xffffffffu, mx[k], o);
+            mn[k] = a < mn[k] ? a : mn[k];
+            mx[k] = b > mx[k] ? b : mx[k];
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomic_min_double(&p.d.bbox[k], mn[k]);
+            atomic_max_double(&p.d.bbox[3 + k], mx[k]);
+        }
+    }
+}
+
+// Exact Q8 semantics for the one case the parallel reduction cannot see: x[0] is the strict
+// maximum.  Then the sequential loop of the reference decides which later elements were ever
+// compared against the running maximum; replay it (one thread, cold path).
+template <int D>
+__global__ void k_bbox_fixup(const Params p) {
+    int k = threadIdx.x;
+    if (k >= D) return;
+    double x0 = p.d.cx[k][0];
+    if (!(x0 > p.d.bbox[3 + k])) return;
+    double mn = DBL_MAX, mx = DBL_MIN;
+    for (int i = 0; i < p.ncur; ++i) {
+        double x = p.d.cx[k][i];
+        if (x < mn)
+            mn = x;
+        else if (x > mx)
+            mx = x;
+    }
+    p.d.bbox[k] = mn;
+    p.d.bbox[3 + k] = mx;
+}
+
+// sums over the CUR set (state) -- V uses omega of the SRT set (same order)
+template <int D>
+__global__ void __launch_bounds__(256) k_sums(const Params p, int n, const double *m, const double *u,
+                                              const double *v0, const double *v1, const double *v2, const double *omega) {
+    double s[6] = {0., 0., 0., 0., 0., 0.};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double mi = m[i], a = v0[i], b = v1[i], c = D == 3 ? v2[i] : 0.;
+        if (omega) s[0] += 1. / omega[i];
+        s[1] += mi;
+        s[2] += D == 3 ? mi * (u[i] + .5 * (a * a + b * b + c * c)) : mi * (u[i] + .5 * (a * a + b * b));
+        s[3] += mi * a;
+        s[4] += mi * b;
+        if (D == 3) s[5] += mi * c;
+    }
+    __shared__ double sh[6][8];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+        if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = s[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double t = 0.;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[threadIdx.x][w];
+        atomicAdd(&p.d.sums[threadIdx.x], t);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_unpermute_f64(const double *src, const int *ids, double *dst, int n, int comps, int stride, int id_base) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[(size_t)(ids[i] - id_base) * stride + comps] = src[i];
+}
+__global__ void __launch_bounds__(256) k_unpermute_i32(const int *src, const int *ids, int *dst, int n, int id_base) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[ids[i] - id_base] = src[i];
+}
+
+} // namespace
+
+int mlh_launch_bbox(mlh_ctx *c) {
+    Params &p = c->p;
+    mlh_prof_begin(c, KID_BBOX);
+    k_bbox_init<<<1, 32, 0, c->stream>>>(p);
+    int blocks = mlh_blocks(p.ncur, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (p.D == 2) {
+        k_bbox<2><<<blocks, 256, 0, c->stream>>>(p);
+        k_bbox_fixup<2><<<1, 32, 0, c->stream>>>(p);
+    } else {
+        k_bbox<3><<<blocks, 256, 0, c->stream>>>(p);
+        k_bbox_fixup<3><<<1, 32, 0, c->stream>>>(p);
+    }
+    mlh_prof_end(c, KID_BBOX);
+    c->launches += 2;
+    MLH_CUDA_CHECK(c, cudaGetLastError());
+    return MLH_OK;
+}
+
+// sums over the current state; which set holds it depends on the phase (see mlh_capi.cu)
+int mlh_launch_sums(mlh_ctx *c) {
+    Params &p = c->p;
+    MLH_CUDA_CHECK(c, cudaMemsetAsync(p.d.sums, 0, 6 * sizeof(double), c->stream));
+    const bool in_srt = c->phase >= 1;
+    int n = in_srt ? (p.own_end - p.own_begin) : p.ncur;
+    int off = in_srt ? p.own_begin : 0;
+    const double *m = in_srt ? p.d.m + off : p.d.cm;
+    const double *u = in_srt ? p.d.u + off : p.d.cu;
+    const double *v0 = in_srt ? p.d.v[0] + off : p.d.cv[0];
+    const double *v1 = in_srt ? p.d.v[1] + off : p.d.cv[1];
+    const double *v2 = p.D == 3 ? (in_srt ? p.d.v[2] + off : p.d.cv[2]) : nullptr;
+    // omega is defined once density has run in this or a previous step; it lives in SRT order, which
+    // is also the order of the CUR set produced from it
+    const double *omega = p.d.omega + p.own_begin;
+    int blocks = mlh_blocks(n, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    mlh_prof_begin(c, KID_SUMS);
+    if (p.D == 2)
+        k_sums<2><<<blocks, 256, 0, c->stream>>>(p, n, m, u, v0, v1, v2, omega);
+    else
+        k_sums<3><<<blocks, 256, 0, c->stream>>>(p, n, m, u, v0, v1, v2, omega);
+    mlh_prof_end(c, KID_SUMS);
+    MLH_CUDA_CHECK(c, cudaGetLastError());
+    return MLH_OK;
+}
+
+int mlh_launch_unpermute_f64(mlh_ctx *c, const double *src, const int *ids, double *dst, int n, int comps, int stride) {
+    mlh_prof_begin(c, KID_UNPERMUTE);
+    k_unpermute_f64<<<mlh_blocks(n, 256), 256, 0, c->stream>>>(src, ids, dst, n, comps, stride, 0);
+    mlh_prof_end(c, KID_UNPERMUTE);
+    MLH_CUDA_CHECK(c, cudaGetLastError());
+    return MLH_OK;
+}
+int mlh_launch_unpermute_i32(mlh_ctx *c, const int *src, const int *ids, int *dst, int n) {
+    mlh_prof_begin(c, KID_UNPERMUTE);
+    k_unpermute_i32<<<mlh_blocks(n, 256), 256, 0, c->stream>>>(src, ids, dst, n, 0);
+    mlh_prof_end(c, KID_UNPERMUTE);
+    MLH_CUDA_CHECK(c, cudaGetLastError());
+    return MLH_OK;
+}

@@ -1,0 +1,224 @@
+// meshlesshydro_b200/csrc/mlh_internal.cuh -- shared by the kernels and the C-ABI layer (not public).
+//
+// Data layout in HBM (all FP64 SoA, one array per scalar component, 32-bit indices):
+//   SRT set: particles sorted by search-grid cell (x fastest), ascending ORIGINAL index inside a
+//            cell == the order of the reference's Cell::prtcls vectors (Particles.cpp:319).
+//            Read by K2..K4.  pos, vel, m, u, id + derived rho, P, omega, cs, Binv(D*D), grad((D+2)*D).
+//   CUR set: the state the next step starts from (output of K4/K5, input of K1), same order as
+//            the SRT set of the step that produced it.
+//   nnl:     neighbour lists, slot-major (entry of slot s of particle i at nnl[s*ncap + i]) so that
+//            one-thread-per-particle kernels read them coalesced.  Slots [0,noi) are regular
+//            neighbours in the reference's list order, slots [noi, noi+noig) periodic images
+//            ("ghosts") ordered by ascending parent original index (== ascending ghost index of
+//            Particles::ghostNNS).  Entry = sorted index j | image code << 26.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include "../../include/mlh_gpu.h"
+
+#define MLH_MAX_D 3
+#define MLH_NNL_IDX_BITS 26
+#define MLH_NNL_IDX_MASK ((1 << MLH_NNL_IDX_BITS) - 1)
+
+// constants of the restated exact Riemann solver (same expressions as oracle/riemann_exact.h:rs_init)
+struct RsConsts {
+    double gamma, gp1d2g, gm1d2g, gm1dgp1, tdgp1, tdgm1, gm1d2, tgdgm1, ginv;
+};
+
+struct Grid {
+    int cells[3];   // global cells per dim (Domain::cellsX/Y/Z); cells[2]=1 in 2D
+    int lcells[3];  // cells of the local grid: == cells except along the slab axis when nranks>1
+    int slab_dim;   // D-1 (slowest-varying axis of the cell id, Particles.cpp:298-302)
+    int layer0;     // global layer index of local layer 0 along slab_dim (may be -1); 0 when nranks==1
+    int sliced;     // 1 when nranks>1 (local grid = owned layers + one halo layer each side)
+    int ncells;     // local cell count
+    double bmin[3], bmax[3], cell_size[3];
+};
+
+struct DevPtrs {
+    // SRT set
+    double *x[3], *v[3], *m, *u, *rho, *P, *omega, *cs;
+    double *B[9];   // Binv row-major as used by the reference (Particles.cpp:1249)
+    double *g[15];  // gradients: field f in {0 rho,1 vx,2 vy,3 vz,4 P}; component a -> g[f*3+a]
+    int *id, *cell, *noi, *noig, *nnl;
+    // CUR set
+    double *cx[3], *cv[3], *cm, *cu;
+    int *cid;
+    // sort scratch
+    int *ckey, *crank, *perm, *cell_count, *cell_start, *scan_tmp;
+    // debug capture (may be null)
+    double *gpre[15];
+    double *flux[5]; // mF, eF, vF[3]
+    // reductions
+    unsigned long long *dt_bits; // min CFL dt as ordered bit pattern
+    double *bbox;                // [0..2] min, [3..5] max over i>=1 (quirk Q8), [6..8] x[0]
+    double *sums;                // 6 doubles
+    unsigned *flags;             // MLH_F_* bits
+    unsigned *counters;          // [0] one-sided seam pairs, [1] faces evaluated
+    double *dt_used;             // dt chosen on device by k_select_dt
+};
+
+struct Params {
+    int D, periodic;
+    int n;          // particles in the SRT set (owned + halo)
+    int own_begin, own_end; // owned range inside the SRT set ([0,n) when nranks==1)
+    int ncur;       // particles in the CUR set
+    int ncap;       // capacity (stride of nnl)
+    int max_ni;
+    int slope_limiting, pairwise, mfm, move_particles, abs_mode, q13_mode, q3_mode, symmetric_seam, debug_capture;
+    double h, hSqr, gamma, cfl, beta, psi1, psi2;
+    double h2, sigma, sigma4; // cubic spline: h/2, normalisation, normalisation/4 (Particles.cpp:10-15)
+    RsConsts rs;
+    Grid grid;
+    DevPtrs d;
+};
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+
+// x*x + y*y (+ z*z) exactly as `pow(dx,2) + pow(dy,2); dSqr += pow(dz,2)` evaluates on the CPU
+// (no FMA contraction): Particles.cpp:342-346.  Bit-exactness of the neighbour sets hangs on this.
+template <int D>
+__device__ __forceinline__ double dist_sqr_exact(const double *d) {
+    double s = __dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1]));
+    if (D == 3) s = __dadd_rn(s, __dmul_rn(d[2], d[2]));
+    return s;
+}
+
+// near-correctly-rounded t^3 (error-compensated) standing in for glibc's pow(t, 3.) at Particles.cpp:20
+__device__ __forceinline__ double cube_cr(double t) {
+    double t2 = __dmul_rn(t, t);
+    double e = __fma_rn(t, t, -t2);
+    return __fma_rn(t2, t, __dmul_rn(e, t));
+}
+
+// Kernel::cubicSpline, Particles.cpp:7-24 (support radius h; h2 = h/2)
+__device__ __forceinline__ double cubic_spline(double r, const Params &p) {
+    double q = __ddiv_rn(r, p.h2);
+    if (q <= 1.) {
+        // sigma*(1.-3./2.*q*q*(1.-q/2.))
+        double a = __dmul_rn(__dmul_rn(1.5, q), q);
+        double b = __dsub_rn(1., __dmul_rn(q, 0.5));
+        return __dmul_rn(p.sigma, __dsub_rn(1., __dmul_rn(a, b)));
+    } else if (q < 2.) {
+        return __dmul_rn(p.sigma4, cube_cr(__dsub_rn(2., q)));
+    }
+    return 0.;
+}
+
+// periodic image of coordinate x with code c (1: parent near the low side, image above max;
+// 2: parent near the high side, image below min) -- Particles.cpp:2123-2142 formulas
+__device__ __forceinline__ double image_coord(double x, int c, double bmin, double bmax) {
+    if (c == 1) return __dadd_rn(bmax, __dsub_rn(x, bmin));
+    if (c == 2) return __dsub_rn(bmin, __dsub_rn(bmax, x));
+    return x;
+}
+// does that image exist?  `x <= min + h` / else-if `max - h < x` (Particles.cpp:2123,2126)
+__device__ __forceinline__ bool image_exists(double x, int c, double bmin, double bmax, double h) {
+    bool low = x <= __dadd_rn(bmin, h);
+    if (c == 1) return low;
+    if (c == 2) return !low && (__dsub_rn(bmax, h) < x);
+    return true;
+}
+__device__ __forceinline__ int reverse_code1(int c) { return c == 1 ? 2 : (c == 2 ? 1 : 0); }
+__device__ __forceinline__ int reverse_code(int code) {
+    return reverse_code1(code & 3) | (reverse_code1((code >> 2) & 3) << 2) | (reverse_code1((code >> 4) & 3) << 4);
+}
+
+// quirk Q1: `abs` at Particles.cpp:1416-1417,1748-1759
+__device__ __forceinline__ double q1_abs(double v, int mode) {
+    if (mode == MLH_ABS_FABS) return fabs(v);
+    int k;
+    if (!(v > -2147483649.0 && v < 2147483648.0))
+        k = INT_MIN; // x86-64 cvttsd2si "integer indefinite"
+    else
+        k = (int)v;  // truncation toward zero
+    if (k < 0) k = (int)(0u - (unsigned)k);
+    return (double)k;
+}
+
+// displacement (neighbour - self) and distance for list entry e of particle i, the way the reference
+// evaluates it for a regular neighbour (Particles.cpp:1170-1175) or a ghost (:2275-2280)
+template <int D, bool PER>
+__device__ __forceinline__ void neighbour_geometry(const Params &p, const double *xi, int e, double *d, double *r) {
+    const int j = e & MLH_NNL_IDX_MASK;
+    double s[3];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double xj = p.d.x[k][j];
+        if (PER) {
+            int ck = (e >> (MLH_NNL_IDX_BITS + 2 * k)) & 3;
+            xj = image_coord(xj, ck, p.grid.bmin[k], p.grid.bmax[k]);
+        }
+        d[k] = __dsub_rn(xj, xi[k]);
+        s[k] = __dsub_rn(xi[k], xj);
+    }
+    *r = sqrt(dist_sqr_exact<D>(s));
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// host-side context
+// ---------------------------------------------------------------------------------------------
+enum KernelId {
+    KID_BBOX = 0, KID_KEY, KID_SCAN, KID_SCATTER, KID_CELLSORT, KID_GATHER, KID_NEIGHBOURS, KID_DENSITY,
+    KID_GRADIENT, KID_SELECT_DT, KID_FLUX, KID_SUMS, KID_UNPERMUTE, KID_HALO, KID_COUNT
+};
+
+struct mlh_ctx {
+    mlh_config cfg;
+    Params p;
+    cudaStream_t stream;
+    long n_owned;        // particles owned by this rank
+    long capacity;
+    bool have_state;     // mlh_upload done
+    int phase;           // 0 = CUR valid (start of step); 1..4 after grid/neighbours/density/gradients
+    void *pool;          // single device allocation backing all arrays
+    size_t pool_bytes;
+    int max_cells;       // allocated cell-array size
+    // pinned host mirror for small readbacks
+    double *h_small;     // pinned
+    unsigned *h_flags;   // pinned
+    char err[512];
+    // profiling
+    bool profiling;
+    cudaEvent_t ev[2 * 64];
+    int ev_kernel[64];
+    int ev_used;
+    double prof_ms[KID_COUNT];
+    long prof_launches[KID_COUNT];
+    long launches;
+    cudaEvent_t timer[2];
+    // multi-GPU
+    void *nccl_comm;
+    int layer_lo, layer_hi; // owned global cell layers along the slab axis
+    int n_layers_global;
+};
+
+// kernel launchers (each .cu implements its stage)
+int mlh_launch_sort(mlh_ctx *c);        // k1_sort.cu
+int mlh_launch_neighbours(mlh_ctx *c);  // k2_neighbours.cu
+int mlh_launch_density(mlh_ctx *c);     // k3_density.cu
+int mlh_launch_gradient(mlh_ctx *c);    // k3b_gradient.cu
+int mlh_launch_flux(mlh_ctx *c, double dt_fixed, double dt_max); // k4_flux.cu
+int mlh_launch_sums(mlh_ctx *c);        // k5_reduce.cu
+int mlh_launch_bbox(mlh_ctx *c);        // k5_reduce.cu
+int mlh_launch_unpermute_f64(mlh_ctx *c, const double *src, const int *ids, double *dst, int n, int comps, int stride); // k5_reduce.cu
+int mlh_launch_unpermute_i32(mlh_ctx *c, const int *src, const int *ids, int *dst, int n);
+
+void mlh_prof_begin(mlh_ctx *c, int kid);
+void mlh_prof_end(mlh_ctx *c, int kid);
+
+#define MLH_CUDA_CHECK(c, expr)                                                                    \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            snprintf((c)->err, sizeof((c)->err), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,     \
+                     cudaGetErrorString(_e));                                                      \
+            return MLH_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+static inline int mlh_blocks(long n, int threads) { return (int)((n + threads - 1) / threads); }
