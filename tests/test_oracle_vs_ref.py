@@ -1,0 +1,43 @@
+"""CPU: restatement vs the reference-source oracle (oracle/_ref) LIVE, on more/larger cases than the
+committed fixtures and over several steps.  Skipped where oracle/_ref was not built (it needs
+/root/reference; prebuilt files travel to the GPU box)."""
+import numpy as np
+import pytest
+
+from meshlesshydro_b200 import ic as IC
+from cpu_oracles import Oracle, Reference, make_config
+
+CASES = [
+    ("kh_random", lambda: IC.kelvin_helmholtz(40, lattice=False), "kh2d", "kh2d", 0, 0.0),
+    ("kh_random_fabs", lambda: IC.kelvin_helmholtz(40, lattice=False), "kh2d", "kh2d_fabs", 1, 0.0),
+    ("kh_lattice_fabs", lambda: IC.kelvin_helmholtz(50), "kh2d", "kh2d_fabs", 1, 0.0),
+    ("fb_jitter", lambda: IC.fluid_block(40, jitter=0.05), "fb2d", "fb2d", 0, 0.0),
+    ("fb_lattice_fabs", lambda: IC.fluid_block(36), "fb2d", "fb2d_fabs", 1, 0.0),
+    ("sedov", lambda: IC.sedov(14), "sedov3d", "sedov3d", 0, 1e-10),
+    ("sedov_fabs", lambda: IC.sedov(14), "sedov3d", "sedov3d_fabs", 1, 1e-10),
+]
+
+
+@pytest.mark.parametrize("name,factory,preset,variant,abs_mode,tol", CASES, ids=[c[0] for c in CASES])
+def test_restatement_equals_reference_sources(name, factory, preset, variant, abs_mode, tol):
+    if not Reference.available(variant):
+        pytest.skip("oracle/_ref/libref_%s.so not built" % variant)
+    ic = factory()
+    orc = Oracle(make_config(preset, ic["h"], ic["gamma"], ic.get("box"), abs_mode=abs_mode), ic)
+    ref = Reference(variant, ic)
+    for step in range(3):
+        dt_o, dt_r = orc.step(), ref.step()
+        assert abs(dt_o - dt_r) <= max(tol, 1e-15) * dt_r
+        assert np.array_equal(orc.fetch("cell"), ref.fetch("cell"))
+        assert np.array_equal(orc.fetch("noi"), ref.fetch("noi"))
+        names = ["x", "y", "vx", "vy", "m", "u", "rho", "P", "omega", "mF", "eF", "vF", "rhoGrad", "vxGrad", "vyGrad", "PGrad"]
+        if ic["dim"] == 3:
+            names += ["z", "vz", "vzGrad"]
+        for k in names:
+            a, b = orc.fetch(k), ref.fetch(k)
+            if tol == 0.0:
+                assert np.array_equal(a, b, equal_nan=True), (name, step, k)
+            else:
+                s = np.nanmax(np.abs(b))
+                err = np.nanmax(np.abs(a - b) / (np.abs(b) + s + 1e-300))
+                assert err <= tol, (name, step, k, err)
