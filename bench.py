@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of the MFV step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one full pass of the hot path (MeshlessScheme::run loop body, phases 1-16: cell sort ->
+neighbour search -> density/matrices -> gradients/limiter/CFL -> faces + exact Riemann -> update) over
+all particles of the workload.  N=1 default workload = BASELINE.json configs[1]: Sedov blast 3D,
+N = 61^3 (synthetic jittered lattice of that shape, seed 6102003; SEAGen/HDF5 are not available).
+N>1: the domain is slab-decomposed (NCCL halo exchange + allreduce-min of dt); weak scaling, the box
+grows to n_side = round(61 * N^(1/3)) so every GPU keeps ~61^3 particles.
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events on the library's
+stream), `e2e` = the same metric through the C ABI with HOST (pinned) buffers: upload + step + download
+every step.  `roofline` describes the dominant kernel (k4_flux_update, FP64-pipe bound),
+`cpu_baseline` the reference's own sources (oracle/_ref) timed on one host core on a bounded sample.
+`--impl reference` times only that CPU reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle_updates_per_s"
+UNIT = "particle-updates/s"
+
+# ---- algorithmic work figures ----
+# doubles read+written per particle-update by the dominant kernel K4+K5
+K4_ALGO_DOUBLES = {2: 24, 3: 38}
+ALL_ALGO_BYTES = {2: 508, 3: 788}
+# FP64 flops the flux kernel needs per face evaluation (DFMA = 2, DADD/DMUL = 1; counted by ncu on the
+# shipped kernel: sm__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on, profiles/r01_*)
+K4_FLOP_PER_FACE = {2: None, 3: None}  # filled from profiles/fp64_per_face.json when present
+
+
+def workloads():
+    from meshlesshydro_b200 import ic as IC
+    return {
+        "sedov61": (lambda n=61: IC.sedov(n), "sedov3d", "Sedov blast 3D MFV, N=61^3 jittered lattice (BASELINE configs[1])"),
+        "sedov128": (lambda: IC.sedov(128), "sedov3d", "Sedov blast 3D MFV, N=128^3"),
+        "sedov256": (lambda: IC.sedov(256), "sedov3d", "Sedov blast 3D MFV, N=256^3 (BASELINE configs[4])"),
+        "kh100": (lambda: IC.kelvin_helmholtz(100, lattice=False), "kh2d", "Kelvin-Helmholtz 2D MFV, N=10^4 random (BASELINE configs[0] shape)"),
+        "kh2000": (lambda: IC.kelvin_helmholtz(2000, lattice=True, jitter=0.2), "kh2d", "Kelvin-Helmholtz 2D MFV, N=4M jittered lattice (BASELINE configs[3])"),
+        "fb1000": (lambda: IC.fluid_block(1000, jitter=0.05), "fb2d", "fluid-block 2D, N=10^6 (BASELINE configs[2])"),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks line")
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0.5 * (max(sm) if sm else 0)]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: the reference's own sources (oracle/_ref), one host core (the reference is serial)
+# ------------------------------------------------------------------------------------------------
+def _ref_variant(preset):
+    return {"sedov3d": "sedov3d_bench", "kh2d": "kh2d_bench", "fb2d": "fb2d"}[preset]
+
+
+def time_reference(ic_factory, preset, n_side, steps, warmup, budget_s):
+    """Times `steps` steps of the reference-source build on a bounded sample: the workload's IC generator
+    at side length n_side, shrunk if one step would blow the time budget.  Returns dict."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cpu_oracles import Reference, Oracle, make_config
+    from meshlesshydro_b200 import ic as IC
+    variant = _ref_variant(preset)
+    gen = {"sedov3d": IC.sedov, "kh2d": lambda n: IC.kelvin_helmholtz(n, lattice=False),
+           "fb2d": lambda n: IC.fluid_block(n, jitter=0.05)}[preset]
+    dim = 3 if preset == "sedov3d" else 2
+    per_particle_s = 3.2e-5 if dim == 3 else 4e-5  # first guess, refined by the first warm-up step
+    kind = "reference" if Reference.available(variant) else "port"
+    while True:
+        n = n_side ** dim
+        est = per_particle_s * n * (steps + warmup)
+        if est <= budget_s or n_side <= 16:
+            break
+        n_side = max(16, int(n_side * (budget_s / est) ** (1.0 / dim)))
+    ic = gen(n_side)
+    n = len(ic["x"])
+    if kind == "reference":
+        arm = Reference(variant, ic)
+    else:
+        arm = Oracle(make_config(preset, ic["h"], ic["gamma"], ic.get("box"), abs_mode=0), ic)
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    for _ in range(warmup):
+        arm.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        arm.step()
+    dt = time.perf_counter() - t0
+    arm.close()
+    return {"value": n * steps / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "%d steps (+%d warm-up) of the same IC generator at N=%d (%s, side %d), %s, %.1f s"
+                      % (steps, warmup, n, preset, n_side,
+                         "oracle/_ref = reference sources g++ -std=c++11 -O3" if kind == "reference" else "oracle/liboracle.so port",
+                         dt),
+            "ms_per_step": 1e3 * dt / steps, "n_particles": n}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    wl = workloads()
+    wname = args.workload or "sedov61"
+    factory, preset, wdesc = wl[wname]
+    n_side_weak = None
+    if world > 1 and wname == "sedov61":
+        n_side_weak = int(round(61 * world ** (1.0 / 3.0)))
+        wdesc = "Sedov blast 3D MFV, weak scaling: N=%d^3 over %d slabs (~61^3 per GPU)" % (n_side_weak, world)
+
+    # ---------------- reference arm ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        side = {"sedov61": 61, "sedov128": 128, "sedov256": 256, "kh100": 100, "kh2000": 2000, "fb1000": 1000}[wname]
+        res = time_reference(factory, preset, n_side_weak or side, max(1, args.steps), max(0, min(args.warmup, 1)), budget_s=150.0)
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wdesc, "n_particles_sample": res["n_particles"]},
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- B200 arm ----------------
+    import torch
+    import torch.distributed as dist
+    from meshlesshydro_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the MFV path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ic = factory(n_side_weak) if n_side_weak else factory()
+    D = ic["dim"]
+    n_total = len(ic["x"])
+    cfg = capi.make_config(preset, ic["h"], ic["gamma"], ic.get("box"), abs_mode=capi.ABS_INT_TRUNC,
+                           q13_mode=capi.Q13_ZERO_Z, max_interactions=128 if D == 3 else 96)
+    cfg.device = local_rank
+    cfg.rank, cfg.nranks = rank, world
+    if world > 1:
+        from meshlesshydro_b200 import multigpu
+        gpu, ic_local = multigpu.create_sharded(cfg, ic, dist)
+    else:
+        gpu, ic_local = capi.MfvGpu(cfg), ic
+        gpu.upload(ic_local)
+    n_local = len(ic_local["x"])
+
+    def barrier():
+        gpu.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        gpu.step(want_dt=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    l0 = gpu.launch_count()
+    barrier()
+    gpu.timer_start()
+    for _ in range(args.steps):
+        gpu.step(want_dt=False)
+    ms = gpu.timer_stop()
+    barrier()
+    launches = gpu.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    flags = gpu.error_flags()
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel profile (separate, untimed pass) for the roofline object ----
+    gpu.profile(True)
+    psteps = max(3, min(args.steps, 10))
+    for _ in range(psteps):
+        gpu.step(want_dt=False)
+    prof = gpu.profile_read()
+    gpu.profile(False)
+    noi_mean = float((gpu.fetch("noi").mean() + gpu.fetch("noiGhosts").mean())) if world == 1 else None
+    top = max(prof.items(), key=lambda kv: kv[1][0])
+    k4_ms = prof["k4_flux_update"][0] / max(1, prof["k4_flux_update"][1])
+    step_ms_prof = sum(v[0] for v in prof.values()) / psteps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    fp64_peak = capi.fp64_peak_tflops(local_rank)
+    fpf = None
+    try:
+        fpf = json.load(open(os.path.join(ROOT, "profiles", "fp64_per_face.json")))["flop_per_face"][str(D)]
+    except Exception:
+        pass
+    faces_per_launch = n_local * noi_mean if noi_mean else None
+    roofline = {"kernel": "k4_flux_update", "bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
+                "peak_source": "DFMA microbenchmark measured live (mlh_measure_fp64_peak)",
+                "achieved": None, "frac": None, "traffic": None,
+                "share_of_step": k4_ms / step_ms_prof if step_ms_prof else None, "ms_per_launch": k4_ms,
+                "faces_per_launch": faces_per_launch, "flop_per_face": fpf}
+    if fpf and faces_per_launch:
+        roofline["achieved"] = fpf * faces_per_launch / (k4_ms * 1e-3) / 1e12
+        roofline["frac"] = roofline["achieved"] / fp64_peak
+    try:
+        roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "fp64_per_face.json")))["dram_bytes_per_launch"].get(wname)
+    except Exception:
+        pass
+    # HBM view of the same kernel and of the whole step (algorithmic bytes)
+    hbm = {"unit": "GB/s", "peak": hbm_peak, "peak_source": hbm_src,
+           "k4_achieved": K4_ALGO_DOUBLES[D] * 8 * n_local / (k4_ms * 1e-3) / 1e9,
+           "step_achieved": ALL_ALGO_BYTES[D] * n_local / (step_ms_prof * 1e-3) / 1e9}
+    hbm["k4_frac"] = hbm["k4_achieved"] / hbm_peak
+    hbm["step_frac"] = hbm["step_achieved"] / hbm_peak
+    kernels = {k: {"ms_per_step": v[0] / psteps, "launches_per_step": v[1] / psteps} for k, v in prof.items() if v[1]}
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e and world == 1:
+        names = ["x", "y", "vx", "vy", "m", "u"] + (["z", "vz"] if D == 3 else [])
+        host = {k: capi.pinned_empty(n_local) for k in names}
+        for k in names:
+            host[k][:] = ic_local[k]
+        host_ic = dict(ic_local)
+        host_ic.update(host)
+        out = {k: (capi.pinned_empty(n_local) if k in names else None) for k in ["x", "y", "z", "vx", "vy", "vz", "m", "u"]}
+        out["ids"] = capi.pinned_empty(n_local, np.int32)
+        esteps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            gpu.upload(host_ic)
+            gpu.step(want_dt=False)
+            gpu.download_state(out)
+        gpu.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            gpu.upload(host_ic)           # H2D of this step's inputs
+            gpu.step(want_dt=False)
+            gpu.download_state(out)       # D2H of the step's result (synchronises)
+            for k in names:               # next step starts from the downloaded state (host round trip)
+                host[k][:] = out[k]
+        e_s = time.perf_counter() - t0
+        nb = len(names) * 8 * n_local
+        e2e = {"value": n_total * esteps / e_s, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb + 4 * n_local,
+               "steps": esteps, "ms_per_step": 1e3 * e_s / esteps, "timing": "host wall clock around upload+step+download, pinned buffers"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        side = {"sedov61": 61, "sedov128": 61, "sedov256": 61, "kh100": 100, "kh2000": 200, "fb1000": 200}[wname]
+        cpu = time_reference(factory, preset, side, 2, 1, budget_s=25.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wdesc, "n_particles": n_total, "dim": D, "mean_neighbours": noi_mean,
+                           "kernel_size": ic["h"], "abs_mode": "INT_TRUNC (g++/libstdc++ build of the reference)",
+                           "l2": "no flush between steps; per-step working set %.0f MB vs 126 MB L2"
+                                 % (n_local * (ALL_ALGO_BYTES[D] + 4 * (noi_mean or 32) * 4) / 1e6),
+                           "parallelism": "slab%d" % world if world > 1 else "single"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "hbm_view": hbm,
+                "kernels": kernels, "cpu_baseline": cpu, "device_flags": flags}
+        print(json.dumps(line))
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -167,6 +167,15 @@ long mlh_launch_count(mlh_ctx *ctx); /* kernels launched by this context so far 
 int mlh_timer_start(mlh_ctx *ctx);
 int mlh_timer_stop(mlh_ctx *ctx, double *ms);
 
+/* pinned (page-locked) host memory for the arrays handed to mlh_upload / mlh_download_state: the
+ * reference's Particles owns plain new[] arrays (Particles.cpp:67-149); a GPU-backed Particles allocates
+ * them here so that the per-step host<->device copies run at full PCIe rate and asynchronously */
+int mlh_host_alloc(unsigned long bytes, void **ptr);
+int mlh_host_free(void *ptr);
+/* measured FP64 (DFMA) peak of a device in TFLOP/s (2 flop per DFMA): the roofline denominator of the
+ * Riemann/flux kernel, which MEASURED_PEAKS.json does not carry */
+int mlh_measure_fp64_peak(int device, double *tflops);
+
 /* ---- multi-GPU (slab decomposition along the slowest cell axis, NCCL halo exchange) ---- */
 #define MLH_NCCL_ID_BYTES 128
 int mlh_comm_unique_id(char *id128);                        /* rank 0: ncclGetUniqueId */

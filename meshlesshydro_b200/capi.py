@@ -80,6 +80,9 @@ def load_library():
         "mlh_comm_unique_id": (C.c_int, [C.c_char_p]),
         "mlh_comm_init": (C.c_int, [vp, C.c_char_p]),
         "mlh_slab_range": (C.c_int, [C.c_int, C.c_int, C.c_int, c_ip, c_ip]),
+        "mlh_host_alloc": (C.c_int, [C.c_ulong, C.POINTER(vp)]),
+        "mlh_host_free": (C.c_int, [vp]),
+        "mlh_measure_fp64_peak": (C.c_int, [C.c_int, c_dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -95,7 +98,7 @@ EXPORTED_SYMBOLS = [
     "mlh_flux_update", "mlh_prepare", "mlh_advance", "mlh_step", "mlh_download_state", "mlh_download_diag", "mlh_sums",
     "mlh_num_particles", "mlh_grid_info", "mlh_debug_fetch", "mlh_stream", "mlh_synchronize", "mlh_profile_enable",
     "mlh_profile_read", "mlh_launch_count", "mlh_timer_start", "mlh_timer_stop", "mlh_comm_unique_id", "mlh_comm_init",
-    "mlh_slab_range",
+    "mlh_slab_range", "mlh_host_alloc", "mlh_host_free", "mlh_measure_fp64_peak",
 ]
 
 _INT_FIELDS = {"cell", "noi", "noiGhosts", "sorted_index", "nnl", "nnlGhosts", "nnlGhostCodes"}
@@ -134,6 +137,30 @@ def make_config(preset, h, gamma, box=None, **over):
         for k, v in enumerate(box):
             cfg.box[k] = float(v)
     return cfg
+
+
+def pinned_empty(n, dtype=np.float64):
+    """numpy array over page-locked host memory from mlh_host_alloc (freed when the array is collected)."""
+    lib = load_library()
+    dt = np.dtype(dtype)
+    nbytes = max(int(n), 1) * dt.itemsize
+    ptr = C.c_void_p()
+    rc = lib.mlh_host_alloc(nbytes, C.byref(ptr))
+    if rc != MLH_OK:
+        raise MlhError("mlh_host_alloc(%d) failed (%d): %s" % (nbytes, rc, lib.mlh_last_error(None).decode()))
+    buf = (C.c_char * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(n))
+    import weakref
+    weakref.finalize(buf, lib.mlh_host_free, ptr)
+    return arr
+
+
+def fp64_peak_tflops(device=0):
+    t = C.c_double()
+    rc = load_library().mlh_measure_fp64_peak(device, C.byref(t))
+    if rc != MLH_OK:
+        raise MlhError("mlh_measure_fp64_peak failed (%d)" % rc)
+    return t.value
 
 
 class MfvGpu:
@@ -176,11 +203,15 @@ class MfvGpu:
             idp = ids.ctypes.data_as(c_ip)
         self._check(self.lib.mlh_upload(self.ctx, self.N, *[_dp(a) for a in arrs], idp), "mlh_upload")
 
-    def download_state(self):
+    def download_state(self, out=None):
+        """current state in original particle order; `out` may hold preallocated (pinned) arrays"""
         n = self.lib.mlh_num_particles(self.ctx)
         names = ["x", "y", "z", "vx", "vy", "vz", "m", "u"]
-        out = {k: (np.empty(n) if (self.D == 3 or k not in ("z", "vz")) else None) for k in names}
-        ids = np.empty(n, dtype=np.int32)
+        if out is None:
+            out = {k: (np.empty(n) if (self.D == 3 or k not in ("z", "vz")) else None) for k in names}
+        ids = out.get("ids")
+        if ids is None:
+            ids = np.empty(n, dtype=np.int32)
         self._check(self.lib.mlh_download_state(self.ctx, *[_dp(out[k]) for k in names], ids.ctypes.data_as(c_ip)),
                     "mlh_download_state")
         out["ids"] = ids

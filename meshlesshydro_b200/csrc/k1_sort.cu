@@ -138,6 +138,13 @@ __global__ void __launch_bounds__(128) k_sort_within_cells(const Params p) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.grid.ncells) return;
     int s = p.d.cell_start[c], e = p.d.cell_start[c + 1];
+    if (e - s > 8 * p.max_ni + 64) {
+        // far more particles in one cell (edge >= h) than any neighbour list can hold: the search would
+        // overflow MAX_NUM_INTERACTIONS anyway (reference: exit(1)); typical cause is a NaN state collapsing
+        // into one cell.  Raise the flag instead of spending O(n^2) here.
+        atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
+        return;
+    }
     for (int a = s + 1; a < e; ++a) {
         int pa = p.d.perm[a];
         int ka = p.d.cid[pa];

@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
                 StencilCell<D> sc = stencil_cell<D, PER>(g, ci, off);
                 if (sc.cell < 0 || sc.code != 0) continue;
                 int s = p.d.cell_start[sc.cell], e = p.d.cell_start[sc.cell + 1];
+                if (e - s > 8 * p.max_ni + 64) { overflow = true; continue; } // collapsed cell (NaN state), see k1
                 for (int j = s; j < e; ++j) {
                     if (j == i) continue;
                     double d[3];

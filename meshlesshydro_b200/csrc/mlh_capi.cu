@@ -167,10 +167,72 @@ static int check_ctx(mlh_ctx *c) {
     return MLH_OK;
 }
 
+__global__ void k_iota(int *dst, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = i;
+}
+
+// DFMA throughput probe: 8 independent chains per thread, `iters` x 8 DFMA each
+__global__ void __launch_bounds__(256) k_dfma_peak(double *sink, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3., x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
+#pragma unroll 4
+    for (int k = 0; k < iters; ++k) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    double t = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (t == 123.456) sink[0] = t; // never true; keeps the chains alive
+}
+
 // ------------------------------------------------------------------------------------------------
 // public API
 // ------------------------------------------------------------------------------------------------
 extern "C" {
+
+int mlh_host_alloc(unsigned long bytes, void **ptr) {
+    if (!ptr || bytes == 0) return MLH_E_INVALID;
+    cudaError_t e = cudaMallocHost(ptr, bytes);
+    if (e != cudaSuccess) {
+        snprintf(g_create_err, sizeof(g_create_err), "cudaMallocHost(%lu) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        *ptr = nullptr;
+        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? MLH_E_NO_DEVICE : MLH_E_CUDA;
+    }
+    return MLH_OK;
+}
+int mlh_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? MLH_OK : MLH_E_CUDA; }
+
+int mlh_measure_fp64_peak(int device, double *tflops) {
+    if (!tflops) return MLH_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return MLH_E_NO_DEVICE; }
+    if (device < 0 || device >= ndev) return MLH_E_INVALID;
+    cudaSetDevice(device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    double *sink = nullptr;
+    if (cudaMalloc(&sink, 64) != cudaSuccess) return MLH_E_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+    double best = 0.;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        k_dfma_peak<<<blocks, 256>>>(sink, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 8.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *tflops = best;
+    return cudaGetLastError() == cudaSuccess ? MLH_OK : MLH_E_CUDA;
+}
 
 int mlh_abi_version(void) { return MLH_ABI_VERSION; }
 
@@ -297,6 +359,7 @@ int mlh_destroy(mlh_ctx *c) {
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     if (c->pool) cudaFree(c->pool);
+    if (c->dl_scratch) cudaFree(c->dl_scratch);
     if (c->p.d.cell_count) {
         cudaFree(c->p.d.cell_count);
         cudaFree(c->p.d.cell_start);
@@ -335,6 +398,8 @@ int mlh_upload(mlh_ctx *c, long N, const double *x, const double *y, const doubl
             cudaStreamSynchronize(c->stream);
             cudaFree(c->pool);
             c->pool = nullptr;
+            if (c->dl_scratch) cudaFree(c->dl_scratch);
+            c->dl_scratch = nullptr;
         }
         p.ncap = (int)cap;
         c->capacity = cap;
@@ -365,10 +430,8 @@ int mlh_upload(mlh_ctx *c, long N, const double *x, const double *y, const doubl
     if (global_ids) {
         MLH_CUDA_CHECK(c, cudaMemcpyAsync(p.d.cid, global_ids, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
     } else {
-        std::vector<int> ids((size_t)N);
-        for (long i = 0; i < N; ++i) ids[(size_t)i] = (int)i;
-        MLH_CUDA_CHECK(c, cudaMemcpyAsync(p.d.cid, ids.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
-        MLH_CUDA_CHECK(c, cudaStreamSynchronize(st));
+        k_iota<<<mlh_blocks(N, 256), 256, 0, st>>>(p.d.cid, (int)N);
+        c->launches++;
     }
     MLH_CUDA_CHECK(c, cudaMemsetAsync(p.d.flags, 0, sizeof(unsigned), st));
     MLH_CUDA_CHECK(c, cudaMemsetAsync(p.d.counters, 0, 4 * sizeof(unsigned), st));
@@ -550,8 +613,8 @@ int mlh_download_state(mlh_ctx *c, double *x, double *y, double *z, double *vx, 
     }
     StateView s = current_state(c);
     const int n = s.n;
-    double *tmp = nullptr;
-    MLH_CUDA_CHECK(c, cudaMalloc(&tmp, sizeof(double) * (size_t)n));
+    // un-permutation scratch: (2D+2) arrays of ncap doubles, allocated once
+    if (!c->dl_scratch) MLH_CUDA_CHECK(c, cudaMalloc(&c->dl_scratch, sizeof(double) * (size_t)c->p.ncap * 8));
     double *hx[3] = {x, y, z}, *hv[3] = {vx, vy, vz};
     struct Item { const double *src; double *dst; } items[8];
     int ni = 0;
@@ -564,29 +627,23 @@ int mlh_download_state(mlh_ctx *c, double *x, double *y, double *z, double *vx, 
     int rc = MLH_OK;
     for (int q = 0; q < ni && rc == MLH_OK; ++q) {
         if (!items[q].dst) continue;
-        if (c->cfg.nranks > 1) {
-            rc = fetch_f64(c, items[q].src, s.ids, n, items[q].dst, 0, 1, tmp);
+        if (c->cfg.nranks > 1) { // device order, ids alongside
+            MLH_CUDA_CHECK(c, cudaMemcpyAsync(items[q].dst, items[q].src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
         } else {
+            double *tmp = c->dl_scratch + (size_t)q * c->p.ncap;
             rc = mlh_launch_unpermute_f64(c, items[q].src, s.ids, tmp, n, 0, 1);
-            if (rc == MLH_OK) {
-                cudaError_t e = cudaMemcpyAsync(items[q].dst, tmp, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-                if (e != cudaSuccess) {
-                    snprintf(c->err, sizeof(c->err), "download failed: %s", cudaGetErrorString(e));
-                    rc = MLH_E_CUDA;
-                }
-            }
+            if (rc == MLH_OK)
+                MLH_CUDA_CHECK(c, cudaMemcpyAsync(items[q].dst, tmp, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
         }
     }
     if (rc == MLH_OK && ids_out) {
         if (c->cfg.nranks > 1) {
-            cudaMemcpyAsync(ids_out, s.ids, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+            MLH_CUDA_CHECK(c, cudaMemcpyAsync(ids_out, s.ids, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
         } else {
             for (int i = 0; i < n; ++i) ids_out[i] = i;
         }
     }
-    cudaStreamSynchronize(c->stream);
-    cudaFree(tmp);
+    MLH_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     return rc;
 }
 

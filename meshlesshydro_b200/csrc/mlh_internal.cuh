@@ -177,6 +177,7 @@ struct mlh_ctx {
     int phase;           // 0 = CUR valid (start of step); 1..4 after grid/neighbours/density/gradients
     void *pool;          // single device allocation backing all arrays
     size_t pool_bytes;
+    double *dl_scratch;  // un-permutation staging of mlh_download_state (8 x ncap doubles, lazily allocated)
     int max_cells;       // allocated cell-array size
     // pinned host mirror for small readbacks
     double *h_small;     // pinned
