@@ -132,12 +132,6 @@ __global__ void __launch_bounds__(256) k_halo_pack(const Params p, int lo, int h
     }
 }
 
-// local bbox contribution with the reference's Q8 semantics expressed on ORIGINAL ids:
-// out[0..2] = min over all, out[3..5] = max over id != 0, out[6..8] = x of id 0 (or -DBL_MAX)
-__global__ void k_bbox_finish_multi(const Params p, double *out9) {
-    // p.d.bbox already holds min (all) and max (CUR index >= 1) -- recomputed here on ids by the caller
-}
-
 int halo_alloc(mlh_ctx *c) {
     if (c->halo_buf) return MLH_OK;
     const Params &p = c->p;
@@ -355,12 +349,5 @@ int mlh_comm_sum(mlh_ctx *c, double *dev, int n) {
     ncclComm_t comm = (ncclComm_t)c->nccl_comm;
     MLH_NCCL_CHECK(c, g_nccl.AllReduce(dev, dev, n, ncclDouble, ncclSum, comm, c->stream));
     c->launches += 1;
-    return MLH_OK;
-}
-
-int mlh_comm_or_flags(mlh_ctx *c) {
-    ncclComm_t comm = (ncclComm_t)c->nccl_comm;
-    // flags are a bit set: max is not an OR, so reduce each rank's word with ncclBor where available
-    MLH_NCCL_CHECK(c, g_nccl.AllReduce(c->p.d.flags, c->p.d.flags + 1, 1, ncclUint32, ncclMax, comm, c->stream));
     return MLH_OK;
 }

@@ -33,11 +33,12 @@ __global__ void k_bbox_init(const Params p) {
     if (k < 3) {
         p.d.bbox[k] = DBL_MAX;      // running minimum starts at numeric_limits::max()  (:230)
         p.d.bbox[3 + k] = DBL_MIN;  // running maximum starts at numeric_limits::min()  (:231, quirk Q2)
+        p.d.bbox[6 + k] = -DBL_MAX; // coordinate of original particle 0 (set by whoever owns it)
     }
 }
 
-// min over all i, max over i >= 1 (x[0] always lowers the minimum first and is never tested
-// against the maximum: `if (x<min) .. else if (x>max)`, :240-244, quirk Q8)
+// min over all particles, max over ORIGINAL index >= 1: x[0] always lowers the running minimum first and is
+// therefore never tested against the maximum (`if (x<min) .. else if (x>max)`, :240-244, quirk Q8)
 template <int D>
 __global__ void __launch_bounds__(256) k_bbox(const Params p) {
     double mn[D], mx[D];
@@ -47,11 +48,13 @@ __global__ void __launch_bounds__(256) k_bbox(const Params p) {
         mx[k] = DBL_MIN;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.ncur; i += gridDim.x * blockDim.x) {
+        const bool first = p.d.cid[i] == 0;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             double x = p.d.cx[k][i];
             mn[k] = x < mn[k] ? x : mn[k];
-            if (i >= 1) mx[k] = x > mx[k] ? x : mx[k];
+            if (!first) mx[k] = x > mx[k] ? x : mx[k];
+            else p.d.bbox[6 + k] = x;
         }
     }
 #pragma unroll
@@ -70,18 +73,21 @@ __global__ void __launch_bounds__(256) k_bbox(const Params p) {
     }
 }
 
-// Exact Q8 semantics for the one case the parallel reduction cannot see: x[0] is the strict
-// maximum.  Then the sequential loop of the reference decides which later elements were ever
-// compared against the running maximum; replay it (one thread, cold path).
+// Exact Q8 semantics for the one case the parallel reduction cannot see: x[0] is the strict maximum
+// along an axis.  Then the sequential loop of the reference decides which later elements were ever
+// compared against the running maximum; replay it in ORIGINAL order (one thread per axis, cold path).
+__global__ void k_inverse_ids(const Params p, int *inv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.ncur) inv[p.d.cid[i]] = i;
+}
 template <int D>
-__global__ void k_bbox_fixup(const Params p) {
+__global__ void k_bbox_replay(const Params p, const int *inv) {
     int k = threadIdx.x;
     if (k >= D) return;
-    double x0 = p.d.cx[k][0];
-    if (!(x0 > p.d.bbox[3 + k])) return;
+    if (!(p.d.bbox[6 + k] > p.d.bbox[3 + k])) return;
     double mn = DBL_MAX, mx = DBL_MIN;
-    for (int i = 0; i < p.ncur; ++i) {
-        double x = p.d.cx[k][i];
+    for (int id = 0; id < p.ncur; ++id) {
+        double x = p.d.cx[k][inv[id]];
         if (x < mn)
             mn = x;
         else if (x > mx)
@@ -139,14 +145,24 @@ int mlh_launch_bbox(mlh_ctx *c) {
     k_bbox_init<<<1, 32, 0, c->stream>>>(p);
     int blocks = mlh_blocks(p.ncur, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    if (p.D == 2) {
+    if (p.D == 2)
         k_bbox<2><<<blocks, 256, 0, c->stream>>>(p);
-        k_bbox_fixup<2><<<1, 32, 0, c->stream>>>(p);
-    } else {
+    else
         k_bbox<3><<<blocks, 256, 0, c->stream>>>(p);
-        k_bbox_fixup<3><<<1, 32, 0, c->stream>>>(p);
-    }
     mlh_prof_end(c, KID_BBOX);
+    c->launches += 1;
+    MLH_CUDA_CHECK(c, cudaGetLastError());
+    return MLH_OK;
+}
+
+// single GPU only (ids are 0..N-1 and all resident); p.d.perm is free before the sort and serves as scratch
+int mlh_launch_bbox_q8_replay(mlh_ctx *c) {
+    Params &p = c->p;
+    k_inverse_ids<<<mlh_blocks(p.ncur, 256), 256, 0, c->stream>>>(p, p.d.perm);
+    if (p.D == 2)
+        k_bbox_replay<2><<<1, 32, 0, c->stream>>>(p, p.d.perm);
+    else
+        k_bbox_replay<3><<<1, 32, 0, c->stream>>>(p, p.d.perm);
     c->launches += 2;
     MLH_CUDA_CHECK(c, cudaGetLastError());
     return MLH_OK;

@@ -358,6 +358,7 @@ int mlh_destroy(mlh_ctx *c) {
     if (!c) return MLH_E_INVALID;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
+    mlh_comm_destroy(c);
     if (c->pool) cudaFree(c->pool);
     if (c->dl_scratch) cudaFree(c->dl_scratch);
     if (c->p.d.cell_count) {
@@ -453,18 +454,36 @@ int mlh_build_grid(mlh_ctx *c) {
         return MLH_E_STATE;
     }
     Params &p = c->p;
+    const bool multi = c->cfg.nranks > 1;
     if (!p.periodic) { // MeshlessScheme.cpp:41-51: grid rebuilt from the particle bounding box every step
         int rc = mlh_launch_bbox(c);
         if (rc != MLH_OK) return rc;
-        MLH_CUDA_CHECK(c, cudaMemcpyAsync(c->h_small, p.d.bbox, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (multi && (rc = mlh_comm_bbox(c)) != MLH_OK) return rc;
+        MLH_CUDA_CHECK(c, cudaMemcpyAsync(c->h_small, p.d.bbox, 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         MLH_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        bool q8 = false; // original particle 0 is the strict maximum along an axis: sequential replay needed
+        for (int k = 0; k < p.D; ++k) q8 = q8 || c->h_small[6 + k] > c->h_small[3 + k];
+        if (q8) {
+            if (multi) {
+                snprintf(c->err, sizeof(c->err), "getDomainLimits quirk Q8 (particle 0 is an axis maximum) is not supported with nranks > 1");
+                return MLH_E_INVALID;
+            }
+            if ((rc = mlh_launch_bbox_q8_replay(c)) != MLH_OK) return rc;
+            MLH_CUDA_CHECK(c, cudaMemcpyAsync(c->h_small, p.d.bbox, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            MLH_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        }
         rc = make_grid(c, c->h_small, c->h_small + 3);
+        if (rc != MLH_OK) return rc;
+    }
+    if (multi) { // exchange 1: boundary layers + migrants (createGhostParticles point of the step)
+        int rc = mlh_halo_exchange_particles(c);
         if (rc != MLH_OK) return rc;
     }
     int rc = mlh_launch_sort(c);
     if (rc != MLH_OK) return rc;
     p.own_begin = 0;
     p.own_end = p.n;
+    if (multi && (rc = mlh_halo_read_layout(c)) != MLH_OK) return rc;
     c->phase = 1;
     return MLH_OK;
 }
@@ -487,6 +506,14 @@ int mlh_density_matrix(mlh_ctx *c) {
         return MLH_E_STATE;
     }
     int rc = mlh_launch_density(c);
+    if (rc == MLH_OK && c->cfg.nranks > 1) { // exchange 2 (updateGhostState point, MeshlessScheme.cpp:109)
+        Params &p = c->p;
+        double *arr[16];
+        int na = 0;
+        arr[na++] = p.d.omega; arr[na++] = p.d.rho; arr[na++] = p.d.P; arr[na++] = p.d.cs;
+        for (int k = 0; k < p.D * p.D; ++k) arr[na++] = p.d.B[k];
+        rc = mlh_halo_refresh(c, arr, na);
+    }
     if (rc == MLH_OK) c->phase = 3;
     return rc;
 }
@@ -498,6 +525,17 @@ int mlh_gradients_limit(mlh_ctx *c) {
         return MLH_E_STATE;
     }
     int rc = mlh_launch_gradient(c);
+    if (rc == MLH_OK && c->cfg.nranks > 1) { // exchange 3 (updateGhostGradients point, :129) + global dt
+        Params &p = c->p;
+        double *arr[16];
+        int na = 0;
+        for (int f = 0; f < 5; ++f) {
+            if (f == 3 && p.D == 2) continue;
+            for (int a = 0; a < p.D; ++a) arr[na++] = p.d.g[f * 3 + a];
+        }
+        rc = mlh_halo_refresh(c, arr, na);
+        if (rc == MLH_OK) rc = mlh_comm_min_dt(c);
+    }
     if (rc == MLH_OK) c->phase = 4;
     return rc;
 }
@@ -700,6 +738,7 @@ int mlh_sums(mlh_ctx *c, double *out6) {
     if (!c->have_state) return MLH_E_STATE;
     int rc = mlh_launch_sums(c);
     if (rc != MLH_OK) return rc;
+    if (c->cfg.nranks > 1 && (rc = mlh_comm_sum(c, c->p.d.sums, 6)) != MLH_OK) return rc;
     MLH_CUDA_CHECK(c, cudaMemcpyAsync(c->h_small, c->p.d.sums, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     MLH_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     for (int k = 0; k < 6; ++k) out6[k] = c->h_small[k];

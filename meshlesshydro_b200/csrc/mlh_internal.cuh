@@ -196,6 +196,12 @@ struct mlh_ctx {
     void *nccl_comm;
     int layer_lo, layer_hi; // owned global cell layers along the slab axis
     int n_layers_global;
+    double *halo_buf;       // exchange-1 send staging: [2 directions][2D+2 fields][halo_cap]
+    int *halo_ids;          // [2][halo_cap]
+    int *halo_counts;       // device: sent dn/up, received dn/up
+    int *h_counts;          // pinned mirror (8 ints)
+    int halo_cap;
+    int lo_layer_end, hi_layer_begin; // owned bottom layer = [own_begin, lo_layer_end), top = [hi_layer_begin, own_end)
 };
 
 // kernel launchers (each .cu implements its stage)
@@ -206,6 +212,15 @@ int mlh_launch_gradient(mlh_ctx *c);    // k3b_gradient.cu
 int mlh_launch_flux(mlh_ctx *c, double dt_fixed, double dt_max); // k4_flux.cu
 int mlh_launch_sums(mlh_ctx *c);        // k5_reduce.cu
 int mlh_launch_bbox(mlh_ctx *c);        // k5_reduce.cu
+int mlh_launch_bbox_q8_replay(mlh_ctx *c); // k5_reduce.cu (rare path of quirk Q8)
+// halo.cu (nranks > 1)
+void mlh_comm_destroy(mlh_ctx *c);
+int mlh_comm_bbox(mlh_ctx *c);
+int mlh_halo_exchange_particles(mlh_ctx *c);
+int mlh_halo_read_layout(mlh_ctx *c);
+int mlh_halo_refresh(mlh_ctx *c, double *const *arrays, int narrays);
+int mlh_comm_min_dt(mlh_ctx *c);
+int mlh_comm_sum(mlh_ctx *c, double *dev, int n);
 int mlh_launch_unpermute_f64(mlh_ctx *c, const double *src, const int *ids, double *dst, int n, int comps, int stride); // k5_reduce.cu
 int mlh_launch_unpermute_i32(mlh_ctx *c, const int *src, const int *ids, int *dst, int n);
 
