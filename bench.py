@@ -12,7 +12,7 @@ grows to n_side = round(61 * N^(1/3)) so every GPU keeps ~61^3 particles.
 
 One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events on the library's
 stream), `e2e` = the same metric through the C ABI with HOST (pinned) buffers: upload + step + download
-every step.  `roofline` describes the dominant kernel (k4_flux_update, FP64-pipe bound),
+every step.  `roofline` describes the dominant kernel (k4b_face_riemann, FP64-pipe bound),
 `cpu_baseline` the reference's own sources (oracle/_ref) timed on one host core on a bounded sample.
 `--impl reference` times only that CPU reference arm.
 """
@@ -260,7 +260,7 @@ def main():
     gpu.profile(False)
     noi_mean = float((gpu.fetch("noi").mean() + gpu.fetch("noiGhosts").mean())) if world == 1 else None
     top = max(prof.items(), key=lambda kv: kv[1][0])
-    k4_ms = prof["k4_flux_update"][0] / max(1, prof["k4_flux_update"][1])
+    k4_ms = prof["k4b_face_riemann"][0] / max(1, prof["k4b_face_riemann"][1])
     step_ms_prof = sum(v[0] for v in prof.values()) / psteps
     peaks = {}
     try:
@@ -276,7 +276,7 @@ def main():
     except Exception:
         pass
     faces_per_launch = n_local * noi_mean if noi_mean else None
-    roofline = {"kernel": "k4_flux_update", "bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
+    roofline = {"kernel": "k4b_face_riemann", "bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
                 "peak_source": "DFMA microbenchmark measured live (mlh_measure_fp64_peak)",
                 "achieved": None, "frac": None, "traffic": None,
                 "share_of_step": k4_ms / step_ms_prof if step_ms_prof else None, "ms_per_launch": k4_ms,

@@ -77,6 +77,9 @@ typedef struct {
     int device;               /* CUDA device ordinal */
     int rank, nranks;         /* slab decomposition over GPUs of one node (nranks<=1: single GPU) */
     long capacity;            /* particle capacity of this rank incl. halo; 0 -> derived from N */
+    long stage_bytes;         /* budget of the per-face staging buffer of the flux pass (it replaces the reference's
+                                 per-slot WijL/WijR/Aij/Fij arrays, Particles.h:201-229); 0 -> 6 GiB.  Particles are
+                                 processed in chunks that fit the budget. */
 } mlh_config;
 
 int mlh_abi_version(void);

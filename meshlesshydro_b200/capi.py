@@ -27,7 +27,8 @@ class MlhConfig(C.Structure):
         "dim", "periodic", "max_interactions", "slope_limiting", "pairwise_limiter", "meshless_finite_mass",
         "move_particles", "abs_mode", "q13_mode", "q3_mode", "symmetric_seam", "debug_capture")] + \
         [(n, C.c_double) for n in ("cfl", "beta", "psi1", "psi2", "kernel_size", "gamma")] + \
-        [("box", C.c_double * 6), ("device", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("capacity", C.c_long)]
+        [("box", C.c_double * 6), ("device", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("capacity", C.c_long),
+         ("stage_bytes", C.c_long)]
 
 
 class MlhError(RuntimeError):

@@ -165,6 +165,12 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
     }
     p.d.noig[i] = ng;
     if (overflow) atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
+    // longest list of this step: bounds the slot loop of the persistent face kernels (k4_flux.cu)
+    {
+        const unsigned am = __activemask();
+        const unsigned len = __reduce_max_sync(am, (unsigned)(nreg + ng));
+        if ((threadIdx.x & 31) == (__ffs(am) - 1)) atomicMax(&p.d.counters[3], len);
+    }
 }
 
 } // namespace
@@ -172,6 +178,7 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
 int mlh_launch_neighbours(mlh_ctx *c) {
     Params &p = c->p;
     int n = p.own_end - p.own_begin;
+    MLH_CUDA_CHECK(c, cudaMemsetAsync(p.d.counters + 3, 0, sizeof(unsigned), c->stream));
     mlh_prof_begin(c, KID_NEIGHBOURS);
     if (p.D == 2 && p.periodic)
         k_neighbours<2, true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);

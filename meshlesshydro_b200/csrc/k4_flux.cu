@@ -8,77 +8,109 @@
 //   Helper::rotationMatrix2D/3D         Helper.cpp:39-77, RiemannSolver::solve (restated, see oracle/riemann_exact.h)
 //   Particles::collectFluxes            :1913-2011, Particles::updateStateAndPosition :2013-2110
 //
-// Gather-side and atomic-free: thread i evaluates every face (i,j) of its own list.  The reference
-// (ENFORCE_FLUX_SYM, quirk Q4) solves a face once, from the endpoint with the LOWER ORIGINAL index,
-// and gives the other endpoint the exact negation; here both endpoint threads evaluate that same
-// canonical orientation (operands are swapped with selects, not branches, so a warp does not
-// diverge on orientation) and the non-canonical one negates.  Both threads therefore add bit-identical
-// +-F and total mass, momentum and energy are conserved to round-off without any exchange.
-// The per-slot buffers of the reference (psijTilde, Aij, WijL/R, Fij, vFrame: ~100 kB per particle,
-// Particles.h:201-229) do not exist: psi-tilde of BOTH endpoints is recomputed from Binv and omega.
+// Three kernels per particle chunk, one thread per FACE EVALUATION in the first two:
+//   k_face_states  (K4a) thread (slot s, particle i): A_ij, boosted + reconstructed + limited + predicted states
+//                        of both endpoints -> face record (4D+5 doubles) in a slot-major staging buffer.
+//                        Gather-bound (both endpoint bundles come through L1/L2), needs ~200 registers.
+//   k_face_riemann (K4b) thread per record: rotate into the face frame, exact Riemann solve, rotate back,
+//                        project -> +-F (D+2 doubles).  Pure FP64; ~100 registers so 5 warps per scheduler
+//                        hide the DFMA/MUFU latencies; its code (one noinline pow, Newton loop with cached
+//                        f/f') stays inside the instruction cache.  [The first version fused all of this
+//                        into one 255-register, 145 KB kernel: ncu showed 56 % of the warp stalls were
+//                        instruction fetches and 14 % FP64-pipe use -- profiles/r01_k4_fused_*.]
+//   k_flux_sum_update (K4c/K5) thread per particle: sum of the slot fluxes in list order, conserved update, drift.
 //
-// Roofline: FP64 pipe (exact Riemann solver: pow/sqrt/div heavy, ~2-3 kFLOP per face, K faces per
-// particle); algorithmic bytes 24 (2D) / 38 (3D) doubles per particle.
+// Gather-side and atomic-free: every face (i,j) is evaluated from BOTH endpoints.  The reference
+// (ENFORCE_FLUX_SYM, quirk Q4) solves a face once, from the endpoint with the LOWER ORIGINAL index, and gives
+// the other endpoint the exact negation; here both endpoint threads evaluate that same canonical orientation
+// (operands swapped with selects) and the non-canonical one negates.  Both add bit-identical +-F, so total
+// mass, momentum and energy are conserved to round-off without any exchange -- also across slab boundaries.
+// The per-slot buffers of the reference (psijTilde, Aij, WijL/R, Fij, vFrame for ALL particles, ~100 kB per
+// particle, Particles.h:201-229) are replaced by the chunk-sized staging buffer.
+//
+// Roofline: K4b is FP64-pipe bound; K4a/K4c are L2/HBM gather passes (staging traffic (5D+7)*8 B per face
+// evaluation, written once and read once).
 #include "mlh_internal.cuh"
 #include <cfloat>
 
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// exact Riemann solver (device restatement; iteration-for-iteration the algorithm of
-// oracle/riemann_exact.h -- Newton-Raphson with Toro's adaptive guess, Brent fallback, sampling at x/t=0)
+// exact Riemann solver (device restatement of oracle/riemann_exact.h: Newton-Raphson with Toro's
+// adaptive guess, Brent fallback, sampling at x/t=0 -- same control flow, same stopping rules).
+// Two deliberate arithmetic differences, both ~1e-15 relative (the bar is 1e-10):
+//   * pow(x,y) = exp(y log x) (one noinline copy) instead of a correctly rounded pow;
+//   * f_K and f_K' are evaluated together at each Newton point and cached, and the identities
+//     x^-(g+1)/2g = x^(g-1)/2g / x,  x^(1/g) = x / (x^(g-1)/2g)^2,  b^(2g/(g-1)) = b^(2/(g-1)) b^2
+//     replace the extra pow calls of the textbook formulas.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double rs_max(double a, double b) { return (a < b) ? b : a; }
 __device__ __forceinline__ double rs_min(double a, double b) { return (b < a) ? b : a; }
 
-__device__ __forceinline__ double rs_fb(const RsConsts &c, double rho, double P, double a, double Pstar) {
-    if (Pstar > P) {
-        double A = c.tdgp1 / rho;
-        double B = c.gm1dgp1 * P;
-        return (Pstar - P) * sqrt(A / (Pstar + B));
+__device__ __noinline__ double mlh_pow(double x, double y) { return x == 0. ? 0. : exp(y * log(x)); }
+
+// f_K(Ps) and (optionally) f_K'(Ps) of BOTH sides, Toro eqs. 4.6/4.7/4.37.  In smooth flow P* lies between
+// PL and PR, i.e. every face has one (weak) shock side and one rarefaction side -- but WHICH side differs from
+// lane to lane.  Evaluating "left, then right" would run the pow and the sqrt twice with half-empty warps;
+// instead each lane first serves its first rarefaction side and its first shock side, whichever they are,
+// and only lanes with two sides of the same kind take a second round.
+struct RsEval {
+    double fL, fR, fpL, fpR, wL, wR; // w_K = (Ps/P_K)^((g-1)/2g), rarefaction sides only
+};
+template <bool NEED_FP>
+__device__ __forceinline__ void rs_eval2(const RsConsts &c, double rhoL, double PL, double aL, double rhoR, double PR,
+                                         double aR, double Ps, RsEval &e) {
+    const bool shL = Ps > PL, shR = Ps > PR;
+    double wL = 0., wR = 0., rL = 0., rR = 0., qL = 0., qR = 0.;
+    if (!shL || !shR) {
+        const bool firstL = !shL;
+        const double r1 = Ps / (firstL ? PL : PR);
+        const double w1 = mlh_pow(r1, c.gm1d2g);
+        if (firstL) { wL = w1; rL = r1; } else { wR = w1; rR = r1; }
+        if (!shL && !shR) {
+            rR = Ps / PR;
+            wR = mlh_pow(rR, c.gm1d2g);
+        }
     }
-    return c.tdgm1 * a * (pow(Pstar / P, c.gm1d2g) - 1.);
-}
-__device__ __forceinline__ double rs_fprimeb(const RsConsts &c, double rho, double P, double a, double Pstar) {
-    if (Pstar > P) {
-        double A = c.tdgp1 / rho;
-        double B = c.gm1dgp1 * P;
-        return (1. - 0.5 * (Pstar - P) / (B + Pstar)) * sqrt(A / (Pstar + B));
+    if (shL || shR) {
+        const bool firstL = shL;
+        const double q1 = sqrt((c.tdgp1 / (firstL ? rhoL : rhoR)) / (Ps + c.gm1dgp1 * (firstL ? PL : PR)));
+        if (firstL) qL = q1; else qR = q1;
+        if (shL && shR) qR = sqrt((c.tdgp1 / rhoR) / (Ps + c.gm1dgp1 * PR));
     }
-    return 1. / (rho * a) * pow(Pstar / P, -c.gp1d2g);
+    e.wL = wL;
+    e.wR = wR;
+    e.fL = shL ? (Ps - PL) * qL : c.tdgm1 * aL * (wL - 1.);
+    e.fR = shR ? (Ps - PR) * qR : c.tdgm1 * aR * (wR - 1.);
+    if (NEED_FP) {
+        // shock: (1 - (Ps-P)/(2(B+Ps))) q      rarefaction: (Ps/P)^-(g+1)/2g / (rho a) = w / (r rho a)
+        const double tL = (shL ? 0.5 * (Ps - PL) : wL) / (shL ? (c.gm1dgp1 * PL + Ps) : (rL * rhoL * aL));
+        const double tR = (shR ? 0.5 * (Ps - PR) : wR) / (shR ? (c.gm1dgp1 * PR + Ps) : (rR * rhoR * aR));
+        e.fpL = shL ? (1. - tL) * qL : tL;
+        e.fpR = shR ? (1. - tR) * qR : tR;
+    }
 }
-__device__ __forceinline__ double rs_f(const RsConsts &c, double rhoL, double uL, double PL, double aL, double rhoR,
-                                       double uR, double PR, double aR, double Pstar) {
-    return rs_fb(c, rhoL, PL, aL, Pstar) + rs_fb(c, rhoR, PR, aR, Pstar) + (uR - uL);
-}
+
 __device__ __forceinline__ double rs_gb(const RsConsts &c, double rho, double P, double Pstar) {
     double A = c.tdgp1 / rho;
     double B = c.gm1dgp1 * P;
     return sqrt(A / (Pstar + B));
 }
-__device__ __forceinline__ double rs_guess_P(const RsConsts &c, double rhoL, double uL, double PL, double aL, double rhoR,
-                                             double uR, double PR, double aR) {
-    double Pguess;
-    double Pmin = rs_min(PL, PR);
-    double Pmax = rs_max(PL, PR);
-    double qmax = Pmax / Pmin;
-    double Ppv = 0.5 * (PL + PR) - 0.125 * (uR - uL) * (PL + PR) * (aL + aR);
-    Ppv = rs_max(5.e-9 * (PL + PR), Ppv);
-    if (qmax <= 2. && Pmin <= Ppv && Ppv <= Pmax) {
-        Pguess = Ppv;
-    } else if (Ppv < Pmin) {
-        Pguess = pow((aL + aR - c.gm1d2 * (uR - uL)) / (aL / pow(PL, c.gm1d2g) + aR / pow(PR, c.gm1d2g)), c.tgdgm1);
-    } else {
-        double gL = rs_gb(c, rhoL, PL, Ppv);
-        double gR = rs_gb(c, rhoR, PR, Ppv);
-        Pguess = (gL * PL + gR * PR - uR + uL) / (gL + gR);
-    }
-    return rs_max(5.e-9 * (PL + PR), Pguess);
+
+__device__ __noinline__ double rs_guess_nonlinear(const RsConsts c, double rhoL, double uL, double PL, double aL, double rhoR,
+                                                  double uR, double PR, double aR, double Ppv, double Pmin) {
+    if (Ppv < Pmin) // two rarefactions
+        return mlh_pow((aL + aR - c.gm1d2 * (uR - uL)) / (aL / mlh_pow(PL, c.gm1d2g) + aR / mlh_pow(PR, c.gm1d2g)), c.tgdgm1);
+    double gL = rs_gb(c, rhoL, PL, Ppv); // two shocks
+    double gR = rs_gb(c, rhoR, PR, Ppv);
+    return (gL * PL + gR * PR - uR + uL) / (gL + gR);
 }
 
-__device__ __noinline__ double rs_brent(const RsConsts cst, double rhoL, double uL, double PL, double aL, double rhoR,
-                                        double uR, double PR, double aR, double lowerlimit, double upperlimit,
-                                        double lowf, double upf) {
+// Brent's method on [lower, upper], f(lower) f(upper) < 0, relative tolerance 5e-9 (a+b): same iterates as
+// oracle/riemann_exact.h:rs_brent (the inverse quadratic step is written over one common denominator).
+// This is a MAIN path: the solver only runs Newton when the initial guess lies below the root.
+__device__ __forceinline__ double rs_brent(const RsConsts &cst, double rhoL, double PL, double aL, double rhoR, double PR,
+                                           double aR, double du, double lowerlimit, double upperlimit, double lowf, double upf) {
     double a = lowerlimit, b = upperlimit, c = 0., d = 1e230;
     double fa = lowf, fb = upf, fc = 0., s = 0., fs = 0.;
     bool mflag;
@@ -92,11 +124,12 @@ __device__ __noinline__ double rs_brent(const RsConsts cst, double rhoL, double 
     mflag = true;
     while (!(fb == 0.) && (fabs(a - b) > 5.e-9 * (a + b))) {
         if ((fa != fc) && (fb != fc)) {
-            s = a * fb * fc / (fa - fb) / (fa - fc) + b * fa * fc / (fb - fa) / (fb - fc) + c * fa * fb / (fc - fa) / (fc - fb);
+            const double dab = fa - fb, dac = fa - fc, dbc = fb - fc;
+            s = (a * fb * fc * dbc - b * fa * fc * dac + c * fa * fb * dab) / (dab * dac * dbc);
         } else {
             s = b - fb * (b - a) / (fb - fa);
         }
-        double tmp2 = 0.25 * (3. * a + b);
+        const double tmp2 = 0.25 * (3. * a + b);
         if (!(((s > tmp2) && (s < b)) || ((s < tmp2) && (s > b))) || (mflag && (fabs(s - b) >= (0.5 * fabs(b - c)))) ||
             (!mflag && (fabs(s - b) >= (0.5 * fabs(c - d)))) || (mflag && (fabs(b - c) < 5.e-9 * (b + c))) ||
             (!mflag && (fabs(c - d) < 5.e-9 * (c + d)))) {
@@ -105,7 +138,9 @@ __device__ __noinline__ double rs_brent(const RsConsts cst, double rhoL, double 
         } else {
             mflag = false;
         }
-        fs = rs_f(cst, rhoL, uL, PL, aL, rhoR, uR, PR, aR, s);
+        RsEval e;
+        rs_eval2<false>(cst, rhoL, PL, aL, rhoR, PR, aR, s, e);
+        fs = e.fL + e.fR + du;
         d = c;
         c = b;
         fc = fb;
@@ -153,9 +188,9 @@ __device__ __noinline__ int rs_solve_vacuum(const RsConsts c, double rhoL, doubl
             double SL = uL + c.tdgm1 * aL;
             if (SL > dxdt) {
                 double base = c.tdgp1 + c.gm1dgp1 * (uL - dxdt) / aL;
-                *rho = rhoL * pow(base, c.tdgm1);
+                *rho = rhoL * mlh_pow(base, c.tdgm1);
                 *u = c.tdgp1 * (aL + c.gm1d2 * uL + dxdt);
-                *P = PL * pow(base, c.tgdgm1);
+                *P = PL * mlh_pow(base, c.tgdgm1);
                 return -1;
             }
             *rho = 0.; *u = 0.; *P = 0.;
@@ -168,9 +203,9 @@ __device__ __noinline__ int rs_solve_vacuum(const RsConsts c, double rhoL, doubl
         double SR = uR - c.tdgm1 * aR;
         if (SR < dxdt) {
             double base = c.tdgp1 - c.gm1dgp1 * (uR - dxdt) / aR;
-            *rho = rhoR * pow(base, c.tdgm1);
+            *rho = rhoR * mlh_pow(base, c.tdgm1);
             *u = c.tdgp1 * (-aR + c.gm1d2 * uR + dxdt);
-            *P = PR * pow(base, c.tgdgm1);
+            *P = PR * mlh_pow(base, c.tgdgm1);
             return 1;
         }
         *rho = 0.; *u = 0.; *P = 0.;
@@ -180,94 +215,110 @@ __device__ __noinline__ int rs_solve_vacuum(const RsConsts c, double rhoL, doubl
     return 1;
 }
 
-// returns +1 (right of the contact sampled), -1 (left), 0 (vacuum); Riemann.cpp:93-127
-__device__ __forceinline__ int rs_solve(const RsConsts &c, double rhoL, double uL, double PL, double rhoR, double uR,
-                                        double PR, double *rhosol, double *usol, double *Psol) {
-    const double dxdt = 0.;
-    if (rhoL == 0. || rhoR == 0.) return rs_solve_vacuum(c, rhoL, uL, PL, rhoR, uR, PR, rhosol, usol, Psol);
-    const double aL = sqrt(c.gamma * PL / rhoL);
-    const double aR = sqrt(c.gamma * PR / rhoR);
-    if (c.tdgm1 * (aL + aR) <= uR - uL) return rs_solve_vacuum(c, rhoL, uL, PL, rhoR, uR, PR, rhosol, usol, Psol);
-    double Pstar = 0.;
-    double Pguess = rs_guess_P(c, rhoL, uL, PL, aL, rhoR, uR, PR, aR);
-    double fPstar = rs_f(c, rhoL, uL, PL, aL, rhoR, uR, PR, aR, Pstar);
-    double fPguess = rs_f(c, rhoL, uL, PL, aL, rhoR, uR, PR, aR, Pguess);
+// The solver is split in three stages so that a thread block can regroup its faces between them
+// (k_face_riemann): setup (sound speeds, vacuum test, initial guess, f at 0 and at the guess), root (Newton /
+// Brent for P*), sample (star state at x/t = 0).  Together they are RiemannSolver::solve (Riemann.cpp:93-94).
+struct RsProblem {
+    double rhoL, PL, aL, rhoR, PR, aR, du; // du = uR - uL
+    double Pguess, fPguess, f0, fpsum;     // f(Pguess), f(0), fL'(Pguess) + fR'(Pguess)
+};
+
+// returns false if the (generated) vacuum path must be taken
+__device__ __forceinline__ bool rs_setup(const RsConsts &c, double rhoL, double uL, double PL, double rhoR, double uR, double PR,
+                                         RsProblem &q) {
+    if (rhoL == 0. || rhoR == 0.) return false;
+    q.rhoL = rhoL; q.PL = PL; q.rhoR = rhoR; q.PR = PR;
+    q.aL = sqrt(c.gamma * PL / rhoL);
+    q.aR = sqrt(c.gamma * PR / rhoR);
+    q.du = uR - uL;
+    if (c.tdgm1 * (q.aL + q.aR) <= q.du) return false;
+    // initial guess (Toro 4.3.2), floored at 5e-9 (PL+PR)
+    const double Pmin = rs_min(PL, PR), Pmax = rs_max(PL, PR);
+    const double qmax = Pmax / Pmin;
+    double Ppv = 0.5 * (PL + PR) - 0.125 * q.du * (PL + PR) * (q.aL + q.aR);
+    Ppv = rs_max(5.e-9 * (PL + PR), Ppv);
+    double Pguess;
+    if (qmax <= 2. && Pmin <= Ppv && Ppv <= Pmax)
+        Pguess = Ppv;
+    else
+        Pguess = rs_guess_nonlinear(c, rhoL, uL, PL, q.aL, rhoR, uR, PR, q.aR, Ppv, Pmin);
+    q.Pguess = rs_max(5.e-9 * (PL + PR), Pguess);
+    // f(0): both sides are rarefactions with (0/P)^.. = 0 exactly  ->  f_K(0) = -2 a_K/(g-1)
+    if (PL > 0. && PR > 0.) {
+        q.f0 = c.tdgm1 * q.aL * (0. - 1.) + c.tdgm1 * q.aR * (0. - 1.) + q.du;
+    } else {
+        RsEval e0;
+        rs_eval2<false>(c, rhoL, PL, q.aL, rhoR, PR, q.aR, 0., e0);
+        q.f0 = e0.fL + e0.fR + q.du;
+    }
+    RsEval e;
+    rs_eval2<true>(c, rhoL, PL, q.aL, rhoR, PR, q.aR, q.Pguess, e);
+    q.fPguess = e.fL + e.fR + q.du;
+    q.fpsum = e.fpL + e.fpR;
+    return true;
+}
+
+__device__ __forceinline__ double rs_root(const RsConsts &c, const RsProblem &q) {
+    double Pstar = 0., fPstar = q.f0, Pguess = q.Pguess, fPguess = q.fPguess, fpsum = q.fpsum;
     if (fPstar * fPguess >= 0.) {
         while (fabs(Pstar - Pguess) > 5.e-9 * (Pstar + Pguess) && fPguess < 0.) {
             Pstar = Pguess;
             fPstar = fPguess;
-            Pguess = Pguess - fPguess / (rs_fprimeb(c, rhoL, PL, aL, Pguess) + rs_fprimeb(c, rhoR, PR, aR, Pguess));
-            fPguess = rs_f(c, rhoL, uL, PL, aL, rhoR, uR, PR, aR, Pguess);
+            Pguess = Pguess - fPguess / fpsum;
+            RsEval e;
+            rs_eval2<true>(c, q.rhoL, q.PL, q.aL, q.rhoR, q.PR, q.aR, Pguess, e);
+            fPguess = e.fL + e.fR + q.du;
+            fpsum = e.fpL + e.fpR;
         }
     }
-    if (1.e6 * fabs(Pstar - Pguess) > 0.5 * (Pstar + Pguess) && fPguess > 0.) {
-        Pstar = rs_brent(c, rhoL, uL, PL, aL, rhoR, uR, PR, aR, Pstar, Pguess, fPstar, fPguess);
-    } else {
-        Pstar = Pguess;
-    }
-    const double ustar = 0.5 * (uL + uR) + 0.5 * (rs_fb(c, rhoR, PR, aR, Pstar) - rs_fb(c, rhoL, PL, aL, Pstar));
-    if (ustar < dxdt) {
-        if (Pstar > PR) { // right shock
-            double PdPR = Pstar / PR;
-            double SR = uR + aR * sqrt(c.gp1d2g * PdPR + c.gm1d2g);
-            if (SR > dxdt) {
-                *rhosol = rhoR * (PdPR + c.gm1dgp1) / (c.gm1dgp1 * PdPR + 1.);
-                *usol = ustar;
-                *Psol = Pstar;
+    if (1.e6 * fabs(Pstar - Pguess) > 0.5 * (Pstar + Pguess) && fPguess > 0.)
+        return rs_brent(c, q.rhoL, q.PL, q.aL, q.rhoR, q.PR, q.aR, q.du, Pstar, Pguess, fPstar, fPguess);
+    return Pguess;
+}
+
+// star state at x/t = 0; returns +1 (right of the contact sampled) or -1 (left); Riemann.cpp:104-127 reads the flag
+__device__ __forceinline__ int rs_sample(const RsConsts &c, const RsProblem &q, double uL, double uR, double Pstar,
+                                         double *rhosol, double *usol, double *Psol) {
+    RsEval e;
+    rs_eval2<false>(c, q.rhoL, q.PL, q.aL, q.rhoR, q.PR, q.aR, Pstar, e);
+    const double ustar = 0.5 * (uL + uR) + 0.5 * (e.fR - e.fL);
+    // one code path serves both sides: right family waves move with u + a.., left with u - a..
+    const bool right = ustar < 0.;
+    const double sg = right ? 1. : -1.;
+    const double uS = right ? uR : uL, aS = right ? q.aR : q.aL, PS = right ? q.PR : q.PL, rhoS = right ? q.rhoR : q.rhoL;
+    const double wS = right ? e.wR : e.wL;
+    double rho_o = rhoS, u_o = uS, P_o = PS;
+    if (Pstar > PS) { // shock
+        const double PdP = Pstar / PS;
+        const double Sspeed = uS + sg * aS * sqrt(c.gp1d2g * PdP + c.gm1d2g);
+        if (right ? (Sspeed > 0.) : (Sspeed < 0.)) {
+            rho_o = rhoS * (PdP + c.gm1dgp1) / (c.gm1dgp1 * PdP + 1.);
+            u_o = ustar;
+            P_o = Pstar;
+        }
+    } else { // rarefaction
+        const double head = uS + sg * aS;
+        if (right ? (head > 0.) : (head < 0.)) {
+            const double PdP = Pstar / PS;
+            const double tail = ustar + sg * aS * wS; // wS = PdP^((g-1)/2g)
+            // right: star state if tail > 0 else fan; left: fan if tail > 0 else star state
+            if (tail > 0. ? right : !right) {
+                rho_o = rhoS * (PdP / (wS * wS)); // PdP^(1/g)
+                u_o = ustar;
+                P_o = Pstar;
             } else {
-                *rhosol = rhoR; *usol = uR; *Psol = PR;
+                const double base = c.tdgp1 - sg * c.gm1dgp1 * uS / aS;
+                const double bp = mlh_pow(base, c.tdgm1);
+                rho_o = rhoS * bp;
+                u_o = c.tdgp1 * (-sg * aS + c.gm1d2 * uS);
+                P_o = PS * (bp * base * base); // base^(2g/(g-1))
             }
-        } else { // right rarefaction
-            double SHR = uR + aR;
-            if (SHR > dxdt) {
-                double PdPR = Pstar / PR;
-                double STR = ustar + aR * pow(PdPR, c.gm1d2g);
-                if (STR > dxdt) {
-                    *rhosol = rhoR * pow(PdPR, c.ginv);
-                    *usol = ustar;
-                    *Psol = Pstar;
-                } else {
-                    double base = c.tdgp1 - c.gm1dgp1 * (uR - dxdt) / aR;
-                    *rhosol = rhoR * pow(base, c.tdgm1);
-                    *usol = c.tdgp1 * (-aR + c.gm1d2 * uR + dxdt);
-                    *Psol = PR * pow(base, c.tgdgm1);
-                }
-            } else {
-                *rhosol = rhoR; *usol = uR; *Psol = PR;
-            }
-        }
-        return 1;
-    }
-    if (Pstar > PL) { // left shock
-        double PdPL = Pstar / PL;
-        double SL = uL - aL * sqrt(c.gp1d2g * PdPL + c.gm1d2g);
-        if (SL < dxdt) {
-            *rhosol = rhoL * (PdPL + c.gm1dgp1) / (c.gm1dgp1 * PdPL + 1.);
-            *usol = ustar;
-            *Psol = Pstar;
-        } else {
-            *rhosol = rhoL; *usol = uL; *Psol = PL;
-        }
-    } else { // left rarefaction
-        double SHL = uL - aL;
-        if (SHL < dxdt) {
-            double PdPL = Pstar / PL;
-            double STL = ustar - aL * pow(PdPL, c.gm1d2g);
-            if (STL > dxdt) {
-                double base = c.tdgp1 + c.gm1dgp1 * (uL - dxdt) / aL;
-                *rhosol = rhoL * pow(base, c.tdgm1);
-                *usol = c.tdgp1 * (aL + c.gm1d2 * uL + dxdt);
-                *Psol = PL * pow(base, c.tgdgm1);
-            } else {
-                *rhosol = rhoL * pow(PdPL, c.ginv);
-                *usol = ustar;
-                *Psol = Pstar;
-            }
-        } else {
-            *rhosol = rhoL; *usol = uL; *Psol = PL;
         }
     }
-    return -1;
+    *rhosol = rho_o;
+    *usol = u_o;
+    *Psol = P_o;
+    return right ? 1 : -1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -317,122 +368,107 @@ __device__ __forceinline__ double dotD(const double *a, const double *b) { // He
     return res;
 }
 
-// Riemann::Riemann + exact + rotateAndProjectFluxes{2D,3D} (Riemann.cpp:7-229).  Wa = state of the
-// canonical particle ("WijR" of the caller = class member WL, the LEFT state of the solver), Wb = the
-// neighbour's ("WijL" = class WR, RIGHT state): quirk Q5.  W = [rho, P, vx, vy(, vz)].
+// Riemann::Riemann (Riemann.cpp:7-81): unit normal of the face and the rotation Lambda taking it to the
+// x axis (Helper::rotationMatrix2D/3D, Helper.cpp:39-77); the L and R velocities are rotated in place.
+// Wa = state of the canonical particle ("WijR" of the caller = class member WL, the LEFT state of the solver),
+// Wb = the neighbour's ("WijL" = class WR, RIGHT state): quirk Q5.  W = [rho, P, vx, vy(, vz)].
+template <int D> struct FaceFrame {
+    double L[D == 2 ? 2 : 9]; // 2D: (ax, ay) of [[ax, ay], [-ay, ax]]; 3D: row-major Rodrigues matrix
+};
 template <int D>
-__device__ __forceinline__ void face_flux(const Params &p, double *Wa, double *Wb, const double *vFrame, const double *A,
-                                          double *F) {
-    const double gamma = p.gamma;
-    const double AijNorm = sqrt(dotD<D>(A, A));
-    double hatA[D];
+__device__ __forceinline__ void face_rotate(const double *A, double *Wa, double *Wb, FaceFrame<D> &fr) {
+    double n2 = 0.;
 #pragma unroll
-    for (int k = 0; k < D; ++k) hatA[k] = 1. / AijNorm * A[k];
-    double rhoSol, PSol, vSol[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) vSol[k] = 0.;
-    int flag;
+    for (int k = 0; k < D; ++k) n2 += A[k] * A[k];
+    const double inv = 1. / sqrt(n2);
     if (D == 2) {
-        // rotationMatrix2D(hatA, unitX): Lambda = [[ax, ay], [-ay, ax]] in the reference's arithmetic
-        double L0 = hatA[0] * 1. + hatA[1] * 0.;
-        double L1 = -(hatA[0] * 0. - hatA[1] * 1.);
-        double L2 = -L1, L3 = L0;
-        double bR0 = Wb[2], bR1 = Wb[3], bL0 = Wa[2], bL1 = Wa[3];
+        const double L0 = inv * A[0], L1 = inv * A[1];
+        fr.L[0] = L0;
+        fr.L[1] = L1;
+        const double bR0 = Wb[2], bR1 = Wb[3], bL0 = Wa[2], bL1 = Wa[3];
         Wb[2] = L0 * bR0 + L1 * bR1;
-        Wb[3] = L2 * bR0 + L3 * bR1;
+        Wb[3] = -L1 * bR0 + L0 * bR1;
         Wa[2] = L0 * bL0 + L1 * bL1;
-        Wa[3] = L2 * bL0 + L3 * bL1;
-        flag = rs_solve(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], &rhoSol, &vSol[0], &PSol);
-        if (flag == 1)
-            vSol[1] = Wb[3];
-        else if (flag == -1)
-            vSol[1] = Wa[3];
-        // rotationMatrix2D(unitX, hatA)
-        double I0 = 1. * hatA[0] + 0. * hatA[1];
-        double I1 = -(1. * hatA[1] - 0. * hatA[0]);
-        double I2 = -I1, I3 = I0;
-        double s0 = vSol[0], s1 = vSol[1];
-        vSol[0] = I0 * s0 + I1 * s1;
-        vSol[1] = I2 * s0 + I3 * s1;
-        F[0] = A[0] * rhoSol * vSol[0] + A[1] * rhoSol * vSol[1];
-        double vLab[2] = {vSol[0] + vFrame[0], vSol[1] + vFrame[1]};
-        if (p.mfm) {
-            vSol[0] = 0.;
-            vSol[1] = 0.;
-        }
-        F[2] = A[0] * (rhoSol * vLab[0] * vSol[0] + PSol) + A[1] * rhoSol * vLab[0] * vSol[1];
-        F[3] = A[0] * rhoSol * vLab[1] * vSol[0] + A[1] * (rhoSol * vLab[1] * vSol[1] + PSol);
-        F[1] = A[0] * (vSol[0] * (PSol / (gamma - 1.) + rhoSol * .5 * dotD<2>(vLab, vLab)) + PSol * vLab[0]) +
-               A[1] * (vSol[1] * (PSol / (gamma - 1.) + rhoSol * .5 * dotD<2>(vLab, vLab)) + PSol * vLab[1]);
+        Wa[3] = -L1 * bL0 + L0 * bL1;
     } else {
-        // rotationMatrix3D(a = hatA, b = unitX): v = a x b, Rodrigues with n = 1/(1+cos) (singular for hatA = -x)
-        double L[9], Li[9];
-        {
-            const double a0 = hatA[0], a1 = hatA[1], a2 = hatA[2];
-            double v0 = a1 * 0. - a2 * 0.;
-            double v1 = a2 * 1. - a0 * 0.;
-            double v2 = a0 * 0. - a1 * 1.;
-            double cosAB = 0. + a0 * 1. + a1 * 0. + a2 * 0.;
-            double n = 1. / (1. + cosAB);
-            L[0] = 1. - n * (v2 * v2 + v1 * v1);
-            L[1] = -v2 + n * v0 * v1;
-            L[2] = v1 + n * v0 * v2;
-            L[3] = v2 + n * v0 * v1;
-            L[4] = 1. - n * (v2 * v2 + v0 * v0);
-            L[5] = -v0 + n * v1 * v2;
-            L[6] = -v1 + n * v0 * v2;
-            L[7] = v0 + n * v1 * v2;
-            L[8] = 1. - n * (v1 * v1 + v0 * v0);
-            // rotationMatrix3D(a = unitX, b = hatA)
-            double w0 = 0. * a2 - 0. * a1;
-            double w1 = 0. * a0 - 1. * a2;
-            double w2 = 1. * a1 - 0. * a0;
-            double cosBA = 0. + 1. * a0 + 0. * a1 + 0. * a2;
-            double m = 1. / (1. + cosBA);
-            Li[0] = 1. - m * (w2 * w2 + w1 * w1);
-            Li[1] = -w2 + m * w0 * w1;
-            Li[2] = w1 + m * w0 * w2;
-            Li[3] = w2 + m * w0 * w1;
-            Li[4] = 1. - m * (w2 * w2 + w0 * w0);
-            Li[5] = -w0 + m * w1 * w2;
-            Li[6] = -w1 + m * w0 * w2;
-            Li[7] = w0 + m * w1 * w2;
-            Li[8] = 1. - m * (w1 * w1 + w0 * w0);
-        }
-        double bR[3] = {Wb[2], Wb[3], Wb[4]}, bL[3] = {Wa[2], Wa[3], Wa[4]};
+        // rotationMatrix3D(a = hatA, b = unitX): v = a x b = (0, a2, -a1), Rodrigues with n = 1/(1+cos)
+        // (singular for hatA = -x, as the reference); rotationMatrix3D(unitX, hatA) is its transpose
+        const double a0 = inv * A[0], a1 = inv * A[1], a2 = inv * A[D - 1];
+        const double v1 = a2, v2 = -a1;
+        const double n = 1. / (1. + a0);
+        double *L = fr.L;
+        L[0] = 1. - n * (v2 * v2 + v1 * v1);
+        L[1] = -v2;
+        L[2] = v1;
+        L[3] = v2;
+        L[4] = 1. - n * (v2 * v2);
+        L[5] = n * v1 * v2;
+        L[6] = -v1;
+        L[7] = n * v1 * v2;
+        L[8] = 1. - n * (v1 * v1);
+        const double bR[3] = {Wb[2], Wb[3], Wb[D + 1]}, bL[3] = {Wa[2], Wa[3], Wa[D + 1]};
         Wb[2] = L[0] * bR[0] + L[1] * bR[1] + L[2] * bR[2];
         Wb[3] = L[3] * bR[0] + L[4] * bR[1] + L[5] * bR[2];
-        Wb[4] = L[6] * bR[0] + L[7] * bR[1] + L[8] * bR[2];
+        Wb[D + 1] = L[6] * bR[0] + L[7] * bR[1] + L[8] * bR[2];
         Wa[2] = L[0] * bL[0] + L[1] * bL[1] + L[2] * bL[2];
         Wa[3] = L[3] * bL[0] + L[4] * bL[1] + L[5] * bL[2];
-        Wa[4] = L[6] * bL[0] + L[7] * bL[1] + L[8] * bL[2];
-        flag = rs_solve(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], &rhoSol, &vSol[0], &PSol);
-        if (flag == 1) {
-            vSol[1] = Wb[3];
-            vSol[2] = Wb[4];
-        } else if (flag == -1) {
-            vSol[1] = Wa[3];
-            vSol[2] = Wa[4];
-        }
-        double s[3] = {vSol[0], vSol[1], vSol[2]};
-        vSol[0] = Li[0] * s[0] + Li[1] * s[1] + Li[2] * s[2];
-        vSol[1] = Li[3] * s[0] + Li[4] * s[1] + Li[5] * s[2];
-        vSol[2] = Li[6] * s[0] + Li[7] * s[1] + Li[8] * s[2];
-        F[0] = A[0] * rhoSol * vSol[0] + A[1] * rhoSol * vSol[1] + A[2] * rhoSol * vSol[2];
-        double vLab[3] = {vSol[0] + vFrame[0], vSol[1] + vFrame[1], vSol[2] + vFrame[2]};
-        if (p.mfm) {
-            vSol[0] = 0.;
-            vSol[1] = 0.;
-            vSol[2] = 0.;
-        }
-        F[2] = A[0] * (rhoSol * vLab[0] * vSol[0] + PSol) + A[1] * rhoSol * vLab[0] * vSol[1] + A[2] * rhoSol * vLab[0] * vSol[2];
-        F[3] = A[0] * rhoSol * vLab[1] * vSol[0] + A[1] * (rhoSol * vLab[1] * vSol[1] + PSol) + A[2] * rhoSol * vLab[1] * vSol[2];
-        F[4] = A[0] * rhoSol * vLab[2] * vSol[0] + A[1] * rhoSol * vLab[2] * vSol[1] + A[2] * (rhoSol * vLab[2] * vSol[2] + PSol);
-        F[1] = A[0] * (vSol[0] * (PSol / (gamma - 1.) + rhoSol * .5 * dotD<3>(vLab, vLab)) + PSol * vLab[0]) +
-               A[1] * (vSol[1] * (PSol / (gamma - 1.) + rhoSol * .5 * dotD<3>(vLab, vLab)) + PSol * vLab[1]) +
-               A[2] * (vSol[2] * (PSol / (gamma - 1.) + rhoSol * .5 * dotD<3>(vLab, vLab)) + PSol * vLab[2]);
+        Wa[D + 1] = L[6] * bL[0] + L[7] * bL[1] + L[8] * bL[2];
     }
-    if (flag == 0) atomicOr(p.d.flags, MLH_F_VACUUM);
+}
+
+// Riemann::exact after the solve (Riemann.cpp:104-141) + rotateAndProjectFluxes{2D,3D} (:144-229): transverse
+// velocity of the sampled side, rotation back, fluxes projected on the un-normalised A.  F = [m, E, px, py(, pz)].
+template <int D>
+__device__ __forceinline__ void face_project(const Params &p, int flag, double rhoSol, double uSol, double PSol, const double *Wa,
+                                             const double *Wb, const FaceFrame<D> &fr, const double *vFrame, const double *A,
+                                             double *F) {
+    const double gamma = p.gamma;
+    double vSol[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) vSol[k] = 0.;
+    vSol[0] = uSol;
+    if (flag == 1) {
+#pragma unroll
+        for (int k = 1; k < D; ++k) vSol[k] = Wb[2 + k];
+    } else if (flag == -1) {
+#pragma unroll
+        for (int k = 1; k < D; ++k) vSol[k] = Wa[2 + k];
+    }
+    if (D == 2) {
+        const double L0 = fr.L[0], L1 = fr.L[1];
+        const double s0 = vSol[0], s1 = vSol[1];
+        vSol[0] = L0 * s0 - L1 * s1; // rotationMatrix2D(unitX, hatA) = [[ax, -ay], [ay, ax]]
+        vSol[1] = L1 * s0 + L0 * s1;
+    } else {
+        const double *L = fr.L;
+        const double s[3] = {vSol[0], vSol[1], vSol[D - 1]};
+        vSol[0] = L[0] * s[0] + L[3] * s[1] + L[6] * s[2];
+        vSol[1] = L[1] * s[0] + L[4] * s[1] + L[7] * s[2];
+        vSol[D - 1] = L[2] * s[0] + L[5] * s[1] + L[8] * s[2];
+    }
+    double vLab[D], Av = 0., v2 = 0.;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        Av += A[k] * rhoSol * vSol[k];
+        vLab[k] = vSol[k] + vFrame[k];
+        v2 += vLab[k] * vLab[k];
+    }
+    F[0] = Av;
+    if (p.mfm) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) vSol[k] = 0.;
+    }
+    const double ekin = PSol / (gamma - 1.) + rhoSol * .5 * v2;
+    double FE = 0.;
+#pragma unroll
+    for (int al = 0; al < D; ++al) {
+        double Fp = A[al] * PSol;
+#pragma unroll
+        for (int be = 0; be < D; ++be) Fp += A[be] * rhoSol * vLab[al] * vSol[be];
+        F[2 + al] = Fp;
+        FE += A[al] * (vSol[al] * ekin + PSol * vLab[al]);
+    }
+    F[1] = FE;
 }
 
 // device-side dt policy (MeshlessScheme.cpp:91-105): fixed dt, or CFL dt clipped to dt_max
@@ -450,77 +486,58 @@ __global__ void k_select_dt(const Params p, double dt_fixed, double dt_max) {
 // W component nu -> gradient field slot: W = [rho, P, vx, vy, vz], slots rho 0, vx 1, vy 2, vz 3, P 4
 __device__ __forceinline__ int w2f(int nu) { return nu == 0 ? 0 : (nu == 1 ? 4 : nu - 1); }
 
+// staging record of one face evaluation: Wa[NW], Wb[NW], vF[D], A[D], sign -> 4D+5 doubles, then F[NW]
+template <int D> struct FaceRec {
+    static constexpr int NW = D + 2;
+    static constexpr int WA = 0, WB = NW, VF = 2 * NW, AA = 2 * NW + D, SG = 2 * NW + 2 * D, NREC = 2 * NW + 2 * D + 1;
+    static constexpr int FX = NREC, NTOT = NREC + NW;
+};
+
+// tile t of a chunk: slot s = t / tiles_per_slot, particles [c0 + 128 (t % tiles_per_slot), +128)
+#define MLH_FACE_TILE 128
+
+// ---------------------------------------------------------------------------------------------
+// K4a: one thread per (slot, particle)
+// ---------------------------------------------------------------------------------------------
 template <int D, bool PER>
-__global__ void __launch_bounds__(128) k_flux_update(const Params p) {
+__global__ void __launch_bounds__(MLH_FACE_TILE) k_face_states(const Params p, double *__restrict__ stage, int c0, int cn, int cstride) {
     constexpr int NW = D + 2;
-    const int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.own_end) return;
+    using R = FaceRec<D>;
+    const int tiles_per_slot = (cn + MLH_FACE_TILE - 1) / MLH_FACE_TILE;
+    const int smax = (int)p.d.counters[3]; // max list length (K2)
+    const int ntiles = tiles_per_slot * smax;
     const double dt = *p.d.dt_used;
     const double gamma = p.gamma;
-
-    // ---- own bundle ----
-    double xs[D], vs[D], Bs[D * D], gs[NW][D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        xs[k] = p.d.x[k][i];
-        vs[k] = p.d.v[k][i];
-    }
-#pragma unroll
-    for (int k = 0; k < D * D; ++k) Bs[k] = p.d.B[k][i];
-#pragma unroll
-    for (int nu = 0; nu < NW; ++nu)
-#pragma unroll
-        for (int k = 0; k < D; ++k) gs[nu][k] = p.d.g[w2f(nu) * 3 + k][i];
-    const double rhos = p.d.rho[i], Ps = p.d.P[i], omgs = p.d.omega[i];
-    const int ids = p.d.id[i];
-    const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
-
-    double acc[NW];
-#pragma unroll
-    for (int nu = 0; nu < NW; ++nu) acc[nu] = 0.;
-
-    for (int s = 0; s < ntot; ++s) {
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int s = t / tiles_per_slot;
+        const int il = (t - s * tiles_per_slot) * MLH_FACE_TILE + threadIdx.x; // index inside the chunk
+        if (il >= cn) continue;
+        const int i = c0 + il;
+        const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
+        if (s >= ntot) continue;
         const int e = p.d.nnl[(size_t)s * p.ncap + i];
         const int j = e & MLH_NNL_IDX_MASK;
         const int code = PER ? (int)((unsigned)e >> MLH_NNL_IDX_BITS) : 0;
-        const int idn = p.d.id[j];
+        const int ids = p.d.id[i], idn = p.d.id[j];
         // canonical orientation: the endpoint with the lower ORIGINAL index plays "i" (Particles.cpp:1841,1889)
         const bool canon = !(idn < ids);
-        // ---- a = canonical endpoint, b = the other; operands selected, not branched ----
-        double xa[D], xb[D], va[D], vb[D], Ba[D * D], Bb[D * D], ga[NW][D], gb[NW][D];
+        const int ia = canon ? i : j, ib = canon ? j : i; // a = canonical endpoint, b = the other
+        double xa[D], xb[D], va[D], vb[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            const double xn = p.d.x[k][j], vn = p.d.v[k][j];
-            xa[k] = canon ? xs[k] : xn;
-            xb[k] = canon ? xn : xs[k];
-            va[k] = canon ? vs[k] : vn;
-            vb[k] = canon ? vn : vs[k];
+            xa[k] = p.d.x[k][ia];
+            xb[k] = p.d.x[k][ib];
+            va[k] = p.d.v[k][ia];
+            vb[k] = p.d.v[k][ib];
         }
-#pragma unroll
-        for (int k = 0; k < D * D; ++k) {
-            const double bn = p.d.B[k][j];
-            Ba[k] = canon ? Bs[k] : bn;
-            Bb[k] = canon ? bn : Bs[k];
-        }
-#pragma unroll
-        for (int nu = 0; nu < NW; ++nu)
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const double gn = p.d.g[w2f(nu) * 3 + k][j];
-                ga[nu][k] = canon ? gs[nu][k] : gn;
-                gb[nu][k] = canon ? gn : gs[nu][k];
-            }
-        const double rhon = p.d.rho[j], Pn = p.d.P[j], omgn = p.d.omega[j];
-        const double rhoa = canon ? rhos : rhon, rhob = canon ? rhon : rhos;
-        const double Pa = canon ? Ps : Pn, Pb = canon ? Pn : Ps;
-        const double omga = canon ? omgs : omgn, omgb = canon ? omgn : omgs;
+        const double rhoa = p.d.rho[ia], rhob = p.d.rho[ib], Pa = p.d.P[ia], Pb = p.d.P[ib];
+        const double omga = p.d.omega[ia], omgb = p.d.omega[ib];
 
         // ---- geometry: b's image as a sees it, a's image as b sees it (identity for regular pairs) ----
         double xbi[D], xai[D];
         if (PER && code != 0) {
             const int cab = canon ? code : reverse_code(code); // code of b's image in a's list
             const int cba = reverse_code(cab);
-            bool ex = true;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 xbi[k] = image_coord(xb[k], (cab >> (2 * k)) & 3, p.grid.bmin[k], p.grid.bmax[k]);
@@ -528,13 +545,15 @@ __global__ void __launch_bounds__(128) k_flux_update(const Params p) {
             }
             // quirk Q9: is the pair also in the OTHER particle's list?  (the view that is not ours)
             {
+                bool ex = true;
                 const int cview = reverse_code(code); // image of self as the neighbour sees it
+                const double *xs = canon ? xa : xb, *xn = canon ? xb : xa;
                 double dd[3];
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
                     const int ck = (cview >> (2 * k)) & 3;
                     ex = ex && image_exists(xs[k], ck, p.grid.bmin[k], p.grid.bmax[k], p.h);
-                    dd[k] = __dsub_rn(image_coord(xs[k], ck, p.grid.bmin[k], p.grid.bmax[k]), p.d.x[k][j]);
+                    dd[k] = __dsub_rn(image_coord(xs[k], ck, p.grid.bmin[k], p.grid.bmax[k]), xn[k]);
                 }
                 ex = ex && (dist_sqr_exact<D>(dd) < p.hSqr);
                 if (!ex && !p.symmetric_seam) atomicAdd(&p.d.counters[0], 1u);
@@ -568,14 +587,22 @@ __global__ void __launch_bounds__(128) k_flux_update(const Params p) {
                 double t1 = 0., t2 = 0.;
 #pragma unroll
                 for (int be = 0; be < D; ++be) {
-                    t1 += Ba[D * al + be] * d1[be] * psi1;
-                    t2 += Bb[D * al + be] * d2[be] * psi2;
+                    t1 += p.d.B[D * al + be][ia] * d1[be] * psi1;
+                    t2 += p.d.B[D * al + be][ib] * d2[be] * psi2;
                 }
                 A[al] = 1. / omga * t1 - 1. / omgb * t2;
             }
         }
 
         // ---- boosted, reconstructed, predicted states (Particles.cpp:1498-1721; ghosts :2546-2672) ----
+        double ga[NW][D], gb[NW][D];
+#pragma unroll
+        for (int nu = 0; nu < NW; ++nu)
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                ga[nu][k] = p.d.g[w2f(nu) * 3 + k][ia];
+                gb[nu][k] = p.d.g[w2f(nu) * 3 + k][ib];
+            }
         double xjxi[3], xijxi[D], xijxj[D], vF[D], Wa[NW], Wb[NW];
         xjxi[2] = 0.; // quirk Q13 (ZERO_Z): never written in the first-order 3D branch
 #pragma unroll
@@ -659,87 +686,270 @@ __global__ void __launch_bounds__(128) k_flux_update(const Params p) {
         }
         if (PER && code != 0 && (Wa[1] < 0. || Wb[1] < 0.)) atomicOr(p.d.flags, MLH_F_NEG_GHOST_PRESSURE);
 
-        // ---- one exact Riemann problem along A, fluxes projected on A ----
-        double F[NW];
-        face_flux<D>(p, Wa, Wb, vF, A, F);
-        const double sgn = canon ? 1. : -1.;
+        // ---- stage the record (slot-major inside the chunk: coalesced here and in K4b/K4c) ----
+        double *rec = stage + (size_t)s * cstride + il;
+        const size_t fs = (size_t)p.max_ni * cstride; // field stride
 #pragma unroll
-        for (int nu = 0; nu < NW; ++nu) acc[nu] += sgn * F[nu]; // collectFluxes, :1926-2008
+        for (int nu = 0; nu < NW; ++nu) {
+            rec[(R::WA + nu) * fs] = Wa[nu];
+            rec[(R::WB + nu) * fs] = Wb[nu];
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            rec[(R::VF + k) * fs] = vF[k];
+            rec[(R::AA + k) * fs] = A[k];
+        }
+        rec[R::SG * fs] = canon ? 1. : -1.;
     }
+}
 
+// ---------------------------------------------------------------------------------------------
+// K4b: one thread per staged record -- the Riemann class of the reference.
+// The root finder has two very different costs per face (Newton: 2-4 evaluations; Brent: ~10, taken whenever
+// the initial guess lies above the root, i.e. for about half of all faces), randomly mixed inside a warp.  So
+// each 128-face tile is regrouped between the solver stages through shared memory: Newton faces are handed to
+// the low threads of the block, Brent faces to the high threads, and at most one warp runs a mixed bag.
+// ---------------------------------------------------------------------------------------------
+#define MLH_RS_FIELDS 11
+template <int D>
+__global__ void __launch_bounds__(MLH_FACE_TILE, 4) k_face_riemann(const Params p, double *__restrict__ stage, int c0, int cn, int cstride) {
+    constexpr int NW = D + 2;
+    constexpr int T = MLH_FACE_TILE;
+    using R = FaceRec<D>;
+    __shared__ double sh[MLH_RS_FIELDS][T]; // solver problem of face `slot`, SoA (conflict-free)
+    __shared__ int sh_item[T];              // work item -> face slot
+    __shared__ int sh_wcount[2][T / 32];
+    const int tiles_per_slot = (cn + T - 1) / T;
+    const int smax = (int)p.d.counters[3];
+    const int ntiles = tiles_per_slot * smax;
+    const size_t fs = (size_t)p.max_ni * cstride;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    bool vacuum = false;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int s = t / tiles_per_slot;
+        const int il = (t - s * tiles_per_slot) * T + tid;
+        const bool valid = il < cn && s < p.d.noi[c0 + (il < cn ? il : 0)] + p.d.noig[c0 + (il < cn ? il : 0)];
+        double *rec = stage + (size_t)s * cstride + il;
+        double Wa[NW], Wb[NW], vF[D], A[D];
+        FaceFrame<D> fr;
+        RsProblem q;
+        double sgn = 0., rhoSol = 0., uSol = 0., PSol = 0.;
+        int flag = 0;
+        int path = 0; // 0: nothing to iterate, 1: Newton first, 2: straight to Brent
+        if (valid) {
+#pragma unroll
+            for (int nu = 0; nu < NW; ++nu) {
+                Wa[nu] = rec[(R::WA + nu) * fs];
+                Wb[nu] = rec[(R::WB + nu) * fs];
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                vF[k] = rec[(R::VF + k) * fs];
+                A[k] = rec[(R::AA + k) * fs];
+            }
+            sgn = rec[R::SG * fs];
+            face_rotate<D>(A, Wa, Wb, fr);
+            // left = canonical particle a, right = b, along +A (Riemann.cpp:93-94)
+            if (rs_setup(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], q)) {
+                path = (q.f0 * q.fPguess >= 0.) ? 1 : 2;
+                sh[0][tid] = q.rhoL; sh[1][tid] = q.PL; sh[2][tid] = q.aL;
+                sh[3][tid] = q.rhoR; sh[4][tid] = q.PR; sh[5][tid] = q.aR;
+                sh[6][tid] = q.du; sh[7][tid] = q.Pguess; sh[8][tid] = q.fPguess;
+                sh[9][tid] = q.f0; sh[10][tid] = q.fpsum;
+            } else {
+                flag = rs_solve_vacuum(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], &rhoSol, &uSol, &PSol);
+                vacuum = vacuum || flag == 0;
+            }
+        }
+        // ---- regroup: Newton items from thread 0 upwards, Brent items from thread T-1 downwards ----
+        const unsigned bN = __ballot_sync(0xffffffffu, path == 1), bB = __ballot_sync(0xffffffffu, path == 2);
+        if (lane == 0) {
+            sh_wcount[0][wid] = __popc(bN);
+            sh_wcount[1][wid] = __popc(bB);
+        }
+        __syncthreads();
+        int offN = 0, offB = 0, nN = 0, nB = 0;
+#pragma unroll
+        for (int w = 0; w < T / 32; ++w) {
+            if (w < wid) {
+                offN += sh_wcount[0][w];
+                offB += sh_wcount[1][w];
+            }
+            nN += sh_wcount[0][w];
+            nB += sh_wcount[1][w];
+        }
+        const unsigned below = (1u << lane) - 1u;
+        if (path == 1) sh_item[offN + __popc(bN & below)] = tid;
+        if (path == 2) sh_item[T - 1 - (offB + __popc(bB & below))] = tid;
+        __syncthreads();
+        if (tid < nN || tid >= T - nB) {
+            const int f = sh_item[tid];
+            RsProblem w;
+            w.rhoL = sh[0][f]; w.PL = sh[1][f]; w.aL = sh[2][f];
+            w.rhoR = sh[3][f]; w.PR = sh[4][f]; w.aR = sh[5][f];
+            w.du = sh[6][f]; w.Pguess = sh[7][f]; w.fPguess = sh[8][f];
+            w.f0 = sh[9][f]; w.fpsum = sh[10][f];
+            sh[7][f] = rs_root(p.rs, w); // P*
+        }
+        __syncthreads();
+        if (valid) {
+            if (path != 0) flag = rs_sample(p.rs, q, Wa[2], Wb[2], sh[7][tid], &rhoSol, &uSol, &PSol);
+            double F[NW];
+            face_project<D>(p, flag, rhoSol, uSol, PSol, Wa, Wb, fr, vF, A, F);
+#pragma unroll
+            for (int nu = 0; nu < NW; ++nu) rec[(R::FX + nu) * fs] = sgn * F[nu];
+        }
+        __syncthreads(); // sh is rewritten by the next tile
+    }
+    if (vacuum) atomicOr(p.d.flags, MLH_F_VACUUM);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4c / K5: collectFluxes (:1926-2008) in list order + updateStateAndPosition (:2013-2110)
+// ---------------------------------------------------------------------------------------------
+template <int D, bool PER>
+__global__ void __launch_bounds__(128) k_flux_sum_update(const Params p, const double *__restrict__ stage, int c0, int cn, int cstride) {
+    constexpr int NW = D + 2;
+    using R = FaceRec<D>;
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= cn) return;
+    const int i = c0 + il;
+    const double dt = *p.d.dt_used;
+    const size_t fs = (size_t)p.max_ni * cstride;
+    const int ntot = p.d.noi[i] + p.d.noig[i];
+    double acc[NW];
+#pragma unroll
+    for (int nu = 0; nu < NW; ++nu) acc[nu] = 0.;
+    for (int s = 0; s < ntot; ++s) {
+        const double *rec = stage + (size_t)s * cstride + il;
+#pragma unroll
+        for (int nu = 0; nu < NW; ++nu) acc[nu] += rec[(R::FX + nu) * fs];
+    }
     if (p.debug_capture) {
         p.d.flux[0][i] = acc[0];
         p.d.flux[1][i] = acc[1];
 #pragma unroll
         for (int k = 0; k < D; ++k) p.d.flux[2 + k][i] = acc[2 + k];
     }
-
-    // ---- K5: updateStateAndPosition, Particles.cpp:2013-2110 ----
-    {
-        double m = p.d.m[i], u = p.d.u[i];
-        double Q[D + 1];
-        double v2 = 0.;
-        if (D == 3)
-            v2 = vs[0] * vs[0] + vs[1] * vs[1] + vs[D - 1] * vs[D - 1];
-        else
-            v2 = vs[0] * vs[0] + vs[1] * vs[1];
-        Q[0] = m * (u + .5 * v2);
+    double xs[D], vs[D];
 #pragma unroll
-        for (int k = 0; k < D; ++k) Q[1 + k] = m * vs[k];
-        if (!p.mfm) m -= dt * acc[0];
-        double vn[D];
+    for (int k = 0; k < D; ++k) {
+        xs[k] = p.d.x[k][i];
+        vs[k] = p.d.v[k][i];
+    }
+    double m = p.d.m[i], u = p.d.u[i];
+    double Q[D + 1];
+    double v2 = 0.;
+    if (D == 3)
+        v2 = vs[0] * vs[0] + vs[1] * vs[1] + vs[D - 1] * vs[D - 1];
+    else
+        v2 = vs[0] * vs[0] + vs[1] * vs[1];
+    Q[0] = m * (u + .5 * v2);
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            Q[1 + k] -= dt * acc[2 + k];
-            vn[k] = Q[1 + k] / m;
-        }
-        Q[0] -= dt * acc[1];
-        if (D == 3)
-            v2 = vn[0] * vn[0] + vn[1] * vn[1] + vn[D - 1] * vn[D - 1];
-        else
-            v2 = vn[0] * vn[0] + vn[1] * vn[1];
-        u = Q[0] / m - .5 * v2;
-        const int o = i - p.own_begin;
+    for (int k = 0; k < D; ++k) Q[1 + k] = m * vs[k];
+    if (!p.mfm) m -= dt * acc[0];
+    double vn[D];
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            double x = xs[k];
-            if (p.move_particles) {
-                x += vs[k] * dt;
-                if (PER) {
-                    if (x < p.grid.bmin[k]) {
-                        x = p.grid.bmax[k] - (p.grid.bmin[k] - x);
-                    } else if (p.grid.bmax[k] <= x) {
-                        x = p.grid.bmin[k] + (x - p.grid.bmax[k]);
-                    }
+    for (int k = 0; k < D; ++k) {
+        Q[1 + k] -= dt * acc[2 + k];
+        vn[k] = Q[1 + k] / m;
+    }
+    Q[0] -= dt * acc[1];
+    if (D == 3)
+        v2 = vn[0] * vn[0] + vn[1] * vn[1] + vn[D - 1] * vn[D - 1];
+    else
+        v2 = vn[0] * vn[0] + vn[1] * vn[1];
+    u = Q[0] / m - .5 * v2;
+    const int o = i - p.own_begin;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double x = xs[k];
+        if (p.move_particles) {
+            x += vs[k] * dt;
+            if (PER) {
+                if (x < p.grid.bmin[k]) {
+                    x = p.grid.bmax[k] - (p.grid.bmin[k] - x);
+                } else if (p.grid.bmax[k] <= x) {
+                    x = p.grid.bmin[k] + (x - p.grid.bmax[k]);
                 }
             }
-            p.d.cx[k][o] = x;
-            p.d.cv[k][o] = vn[k];
         }
-        p.d.cm[o] = m;
-        p.d.cu[o] = u;
-        p.d.cid[o] = ids;
+        p.d.cx[k][o] = x;
+        p.d.cv[k][o] = vn[k];
     }
+    p.d.cm[o] = m;
+    p.d.cu[o] = u;
+    p.d.cid[o] = p.d.id[i];
+}
+
+template <int D, bool PER>
+int launch_chunks(mlh_ctx *c) {
+    Params &p = c->p;
+    const int n = p.own_end - p.own_begin;
+    const int chunk = c->stage_chunk;
+    const int grid_persistent = c->num_sms * 8;
+    cudaStream_t st = c->stream;
+    for (int b = 0; b < n; b += chunk) {
+        const int cn = (n - b < chunk) ? n - b : chunk;
+        const int c0 = p.own_begin + b;
+        mlh_prof_begin(c, KID_FACES);
+        k_face_states<D, PER><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, c0, cn, chunk);
+        mlh_prof_end(c, KID_FACES);
+        mlh_prof_begin(c, KID_FLUX);
+        k_face_riemann<D><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, c0, cn, chunk);
+        mlh_prof_end(c, KID_FLUX);
+        mlh_prof_begin(c, KID_UPDATE);
+        k_flux_sum_update<D, PER><<<mlh_blocks(cn, 128), 128, 0, st>>>(p, c->stage, c0, cn, chunk);
+        mlh_prof_end(c, KID_UPDATE);
+    }
+    return MLH_OK;
 }
 
 } // namespace
 
+// staging buffer: (5D+7) doubles per (slot, particle) of one chunk
+int mlh_stage_alloc(mlh_ctx *c) {
+    Params &p = c->p;
+    const size_t per_particle = (size_t)(5 * p.D + 7) * sizeof(double) * (size_t)p.max_ni;
+    size_t budget = c->cfg.stage_bytes > 0 ? (size_t)c->cfg.stage_bytes : ((size_t)6 << 30);
+    long chunk = (long)(budget / per_particle);
+    chunk = chunk / MLH_FACE_TILE * MLH_FACE_TILE;
+    if (chunk < 4 * MLH_FACE_TILE) chunk = 4 * MLH_FACE_TILE;
+    long need = ((long)p.ncap + MLH_FACE_TILE - 1) / MLH_FACE_TILE * MLH_FACE_TILE;
+    if (chunk > need) chunk = need;
+    if (c->stage && chunk == c->stage_chunk) return MLH_OK;
+    if (c->stage) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(c->stage);
+        c->stage = nullptr;
+    }
+    cudaError_t e = cudaMalloc(&c->stage, per_particle * (size_t)chunk);
+    if (e != cudaSuccess) {
+        snprintf(c->err, sizeof(c->err), "cudaMalloc of the %.2f GB face staging buffer failed: %s (lower mlh_config.stage_bytes)",
+                 per_particle * (double)chunk / 1e9, cudaGetErrorString(e));
+        cudaGetLastError();
+        return MLH_E_CUDA;
+    }
+    c->stage_chunk = (int)chunk;
+    return MLH_OK;
+}
+
 int mlh_launch_flux(mlh_ctx *c, double dt_fixed, double dt_max) {
     Params &p = c->p;
     int n = p.own_end - p.own_begin;
+    int rc = mlh_stage_alloc(c);
+    if (rc != MLH_OK) return rc;
     mlh_prof_begin(c, KID_SELECT_DT);
     k_select_dt<<<1, 1, 0, c->stream>>>(p, dt_fixed, dt_max);
     mlh_prof_end(c, KID_SELECT_DT);
-    mlh_prof_begin(c, KID_FLUX);
     if (p.D == 2 && p.periodic)
-        k_flux_update<2, true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+        launch_chunks<2, true>(c);
     else if (p.D == 2)
-        k_flux_update<2, false><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+        launch_chunks<2, false>(c);
     else if (p.periodic)
-        k_flux_update<3, true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+        launch_chunks<3, true>(c);
     else
-        k_flux_update<3, false><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
-    mlh_prof_end(c, KID_FLUX);
+        launch_chunks<3, false>(c);
     MLH_CUDA_CHECK(c, cudaGetLastError());
     p.ncur = n;
     return MLH_OK;

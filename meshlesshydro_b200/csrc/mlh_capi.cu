@@ -16,7 +16,8 @@ static char g_create_err[512] = "";
 static const char *kKernelNames[KID_COUNT] = {
     "k0_bbox",        "k1_cell_key",   "k1_scan",        "k1_scatter_perm", "k1_sort_within_cells",
     "k1_gather",      "k2_neighbours", "k3_density_matrix", "k3b_gradient_limit", "k4_select_dt",
-    "k4_flux_update", "k5_sums",       "k5_unpermute",   "halo_exchange"};
+    "k4a_face_states", "k4b_face_riemann", "k4c_flux_sum_update", "k5_sums", "k5_unpermute", "halo_exchange"};
+static_assert(sizeof(kKernelNames) / sizeof(kKernelNames[0]) == KID_COUNT, "one name per KernelId");
 
 // ------------------------------------------------------------------------------------------------
 // profiling brackets (CUDA events on the context's stream)
@@ -289,6 +290,11 @@ int mlh_create(const mlh_config *cfg, mlh_ctx **out) {
     if (c->cfg.nranks < 1) c->cfg.nranks = 1;
     if (c->cfg.max_interactions <= 0) c->cfg.max_interactions = 128;
     cudaSetDevice(cfg->device);
+    {
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, cfg->device);
+        c->num_sms = prop.multiProcessorCount; // 148 on B200: persistent kernels launch a multiple of it
+    }
     Params &p = c->p;
     p.D = cfg->dim;
     p.periodic = cfg->periodic ? 1 : 0;
@@ -361,6 +367,7 @@ int mlh_destroy(mlh_ctx *c) {
     mlh_comm_destroy(c);
     if (c->pool) cudaFree(c->pool);
     if (c->dl_scratch) cudaFree(c->dl_scratch);
+    if (c->stage) cudaFree(c->stage);
     if (c->p.d.cell_count) {
         cudaFree(c->p.d.cell_count);
         cudaFree(c->p.d.cell_start);

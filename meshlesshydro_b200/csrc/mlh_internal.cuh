@@ -55,7 +55,7 @@ struct DevPtrs {
     double *bbox;                // [0..2] min, [3..5] max over i>=1 (quirk Q8), [6..8] x[0]
     double *sums;                // 6 doubles
     unsigned *flags;             // MLH_F_* bits
-    unsigned *counters;          // [0] one-sided seam pairs, [1] faces evaluated
+    unsigned *counters;          // [0] one-sided seam pairs, [3] longest neighbour list of this step (K2)
     double *dt_used;             // dt chosen on device by k_select_dt
 };
 
@@ -164,7 +164,7 @@ __device__ __forceinline__ void neighbour_geometry(const Params &p, const double
 // ---------------------------------------------------------------------------------------------
 enum KernelId {
     KID_BBOX = 0, KID_KEY, KID_SCAN, KID_SCATTER, KID_CELLSORT, KID_GATHER, KID_NEIGHBOURS, KID_DENSITY,
-    KID_GRADIENT, KID_SELECT_DT, KID_FLUX, KID_SUMS, KID_UNPERMUTE, KID_HALO, KID_COUNT
+    KID_GRADIENT, KID_SELECT_DT, KID_FACES, KID_FLUX, KID_UPDATE, KID_SUMS, KID_UNPERMUTE, KID_HALO, KID_COUNT
 };
 
 struct mlh_ctx {
@@ -177,6 +177,9 @@ struct mlh_ctx {
     int phase;           // 0 = CUR valid (start of step); 1..4 after grid/neighbours/density/gradients
     void *pool;          // single device allocation backing all arrays
     size_t pool_bytes;
+    double *stage;       // face staging buffer of K4 (k4_flux.cu): (5D+7) doubles x max_ni x stage_chunk
+    int stage_chunk;     // particles per K4 chunk (multiple of 128)
+    int num_sms;
     double *dl_scratch;  // un-permutation staging of mlh_download_state (8 x ncap doubles, lazily allocated)
     int max_cells;       // allocated cell-array size
     // pinned host mirror for small readbacks
