@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmlh_gpu.so")
+LIB_PATH = os.environ.get("MLH_GPU_LIB") or os.path.join(_HERE, "libmlh_gpu.so")  # override: A/B builds of the kernels
 
 MLH_OK = 0
 ABS_INT_TRUNC, ABS_FABS = 0, 1

@@ -106,57 +106,117 @@ __device__ __noinline__ double rs_guess_nonlinear(const RsConsts c, double rhoL,
     return (gL * PL + gR * PR - uR + uL) / (gL + gR);
 }
 
-// Brent's method on [lower, upper], f(lower) f(upper) < 0, relative tolerance 5e-9 (a+b): same iterates as
-// oracle/riemann_exact.h:rs_brent (the inverse quadratic step is written over one common denominator).
-// This is a MAIN path: the solver only runs Newton when the initial guess lies below the root.
-__device__ __forceinline__ double rs_brent(const RsConsts &cst, double rhoL, double PL, double aL, double rhoR, double PR,
-                                           double aR, double du, double lowerlimit, double upperlimit, double lowf, double upf) {
-    double a = lowerlimit, b = upperlimit, c = 0., d = 1e230;
-    double fa = lowf, fb = upf, fc = 0., s = 0., fs = 0.;
-    bool mflag;
-    if (fa * fb > 0.) return b;
+struct RsProblem {
+    double rhoL, PL, aL, rhoR, PR, aR, du; // du = uR - uL
+    double Pguess, fPguess, f0, fpsum;     // f(Pguess), f(0), fL'(Pguess) + fR'(Pguess)
+};
+
+// Root finder as a resumable state machine: one call of rs_iter_step() = one new trial pressure + one
+// evaluation of f, for either method.  Control flow and iterates are those of oracle/riemann_exact.h
+// (rs_solve's Newton loop, then rs_brent; the inverse quadratic step is written over one common
+// denominator).  Brent is a MAIN path: Newton only runs when the initial guess lies below the root,
+// which is the minority of faces, and Brent's iteration count has a long tail (3..20) -- hence the
+// per-iteration regrouping in k_face_riemann.
+//   Newton fields: a = Pstar, fa = f(Pstar), b = Pguess, fb = f(Pguess), c = fL'(Pguess) + fR'(Pguess)
+//   Brent fields:  a, b, c, d, fa, fb, fc, mflag as in the textbook
+enum { RS_DONE = 0, RS_NEWTON = 1, RS_BRENT = 2 };
+struct RsIter {
+    double a, b, c, d, fa, fb, fc;
+    int method, mflag;
+};
+
+// enter Brent on [lower, upper]; returns false if it terminates immediately (result in it.b)
+__device__ __forceinline__ bool rs_brent_begin(RsIter &it, double lower, double upper, double lowf, double upf) {
+    double a = lower, b = upper, fa = lowf, fb = upf;
+    it.method = RS_DONE;
+    it.b = b;
+    if (fa * fb > 0.) return false; // not bracketed: keep upper (as the oracle)
     if (fabs(fa) < fabs(fb)) {
         double t = a; a = b; b = t;
         t = fa; fa = fb; fb = t;
     }
-    c = a;
-    fc = fa;
-    mflag = true;
-    while (!(fb == 0.) && (fabs(a - b) > 5.e-9 * (a + b))) {
-        if ((fa != fc) && (fb != fc)) {
-            const double dab = fa - fb, dac = fa - fc, dbc = fb - fc;
-            s = (a * fb * fc * dbc - b * fa * fc * dac + c * fa * fb * dab) / (dab * dac * dbc);
-        } else {
-            s = b - fb * (b - a) / (fb - fa);
-        }
-        const double tmp2 = 0.25 * (3. * a + b);
-        if (!(((s > tmp2) && (s < b)) || ((s < tmp2) && (s > b))) || (mflag && (fabs(s - b) >= (0.5 * fabs(b - c)))) ||
-            (!mflag && (fabs(s - b) >= (0.5 * fabs(c - d)))) || (mflag && (fabs(b - c) < 5.e-9 * (b + c))) ||
-            (!mflag && (fabs(c - d) < 5.e-9 * (c + d)))) {
-            s = 0.5 * (a + b);
-            mflag = true;
-        } else {
-            mflag = false;
-        }
-        RsEval e;
-        rs_eval2<false>(cst, rhoL, PL, aL, rhoR, PR, aR, s, e);
-        fs = e.fL + e.fR + du;
-        d = c;
-        c = b;
-        fc = fb;
-        if (fa * fs < 0.) {
-            b = s;
-            fb = fs;
-        } else {
-            a = s;
-            fa = fs;
-        }
-        if (fabs(fa) < fabs(fb)) {
-            double t = a; a = b; b = t;
-            t = fa; fa = fb; fb = t;
+    it.a = a; it.b = b; it.fa = fa; it.fb = fb;
+    it.c = a; it.fc = fa; it.d = 1e230; it.mflag = 1;
+    if (!(fb == 0.) && (fabs(a - b) > 5.e-9 * (a + b))) {
+        it.method = RS_BRENT;
+        return true;
+    }
+    return false;
+}
+
+// after rs_setup: which method runs first (the oracle's `if (fPstar*fPguess >= 0)` / Brent test)
+__device__ __forceinline__ void rs_iter_begin(const RsProblem &q, RsIter &it) {
+    const double Pstar = 0., fPstar = q.f0, Pguess = q.Pguess, fPguess = q.fPguess;
+    it.method = RS_DONE;
+    it.mflag = 0;
+    it.b = Pguess;
+    it.a = Pstar; it.fa = fPstar; it.fb = fPguess; it.c = q.fpsum; it.d = 0.; it.fc = 0.;
+    if (fPstar * fPguess >= 0.) {
+        if (fabs(Pstar - Pguess) > 5.e-9 * (Pstar + Pguess) && fPguess < 0.) {
+            it.method = RS_NEWTON;
+            return;
         }
     }
-    return b;
+    if (1.e6 * fabs(Pstar - Pguess) > 0.5 * (Pstar + Pguess) && fPguess > 0.) rs_brent_begin(it, Pstar, Pguess, fPstar, fPguess);
+}
+
+// trial pressure of this iteration
+__device__ __forceinline__ double rs_iter_trial(RsIter &it) {
+    if (it.method == RS_NEWTON) {
+        it.a = it.b; // Pstar = Pguess
+        it.fa = it.fb;
+        it.b = it.b - it.fb / it.c;
+        return it.b;
+    }
+    const double a = it.a, b = it.b, c = it.c, d = it.d, fa = it.fa, fb = it.fb, fc = it.fc;
+    const bool mflag = it.mflag != 0;
+    double s;
+    if ((fa != fc) && (fb != fc)) {
+        const double dab = fa - fb, dac = fa - fc, dbc = fb - fc;
+        s = (a * fb * fc * dbc - b * fa * fc * dac + c * fa * fb * dab) / (dab * dac * dbc);
+    } else {
+        s = b - fb * (b - a) / (fb - fa);
+    }
+    const double tmp2 = 0.25 * (3. * a + b);
+    if (!(((s > tmp2) && (s < b)) || ((s < tmp2) && (s > b))) || (mflag && (fabs(s - b) >= (0.5 * fabs(b - c)))) ||
+        (!mflag && (fabs(s - b) >= (0.5 * fabs(c - d)))) || (mflag && (fabs(b - c) < 5.e-9 * (b + c))) ||
+        (!mflag && (fabs(c - d) < 5.e-9 * (c + d)))) {
+        s = 0.5 * (a + b);
+        it.mflag = 1;
+    } else {
+        it.mflag = 0;
+    }
+    return s;
+}
+
+// digest f(s) (and f'(s) for Newton); afterwards it.method == RS_DONE means P* = it.b
+__device__ __forceinline__ void rs_iter_update(RsIter &it, double s, double fs, double fps) {
+    if (it.method == RS_NEWTON) {
+        it.fb = fs;
+        it.c = fps;
+        const double Pstar = it.a, Pguess = it.b;
+        if (fabs(Pstar - Pguess) > 5.e-9 * (Pstar + Pguess) && fs < 0.) return; // next Newton iteration
+        it.method = RS_DONE;
+        if (1.e6 * fabs(Pstar - Pguess) > 0.5 * (Pstar + Pguess) && fs > 0.) rs_brent_begin(it, Pstar, Pguess, it.fa, fs);
+        return;
+    }
+    double a = it.a, b = it.b, fa = it.fa, fb = it.fb;
+    it.d = it.c;
+    it.c = b;
+    it.fc = fb;
+    if (fa * fs < 0.) {
+        b = s;
+        fb = fs;
+    } else {
+        a = s;
+        fa = fs;
+    }
+    if (fabs(fa) < fabs(fb)) {
+        double t = a; a = b; b = t;
+        t = fa; fa = fb; fb = t;
+    }
+    it.a = a; it.b = b; it.fa = fa; it.fb = fb;
+    if (!(!(fb == 0.) && (fabs(a - b) > 5.e-9 * (a + b)))) it.method = RS_DONE;
 }
 
 // vacuum sampling (Toro 4.6); cold path
@@ -218,10 +278,6 @@ __device__ __noinline__ int rs_solve_vacuum(const RsConsts c, double rhoL, doubl
 // The solver is split in three stages so that a thread block can regroup its faces between them
 // (k_face_riemann): setup (sound speeds, vacuum test, initial guess, f at 0 and at the guess), root (Newton /
 // Brent for P*), sample (star state at x/t = 0).  Together they are RiemannSolver::solve (Riemann.cpp:93-94).
-struct RsProblem {
-    double rhoL, PL, aL, rhoR, PR, aR, du; // du = uR - uL
-    double Pguess, fPguess, f0, fpsum;     // f(Pguess), f(0), fL'(Pguess) + fR'(Pguess)
-};
 
 // returns false if the (generated) vacuum path must be taken
 __device__ __forceinline__ bool rs_setup(const RsConsts &c, double rhoL, double uL, double PL, double rhoR, double uR, double PR,
@@ -256,24 +312,6 @@ __device__ __forceinline__ bool rs_setup(const RsConsts &c, double rhoL, double 
     q.fPguess = e.fL + e.fR + q.du;
     q.fpsum = e.fpL + e.fpR;
     return true;
-}
-
-__device__ __forceinline__ double rs_root(const RsConsts &c, const RsProblem &q) {
-    double Pstar = 0., fPstar = q.f0, Pguess = q.Pguess, fPguess = q.fPguess, fpsum = q.fpsum;
-    if (fPstar * fPguess >= 0.) {
-        while (fabs(Pstar - Pguess) > 5.e-9 * (Pstar + Pguess) && fPguess < 0.) {
-            Pstar = Pguess;
-            fPstar = fPguess;
-            Pguess = Pguess - fPguess / fpsum;
-            RsEval e;
-            rs_eval2<true>(c, q.rhoL, q.PL, q.aL, q.rhoR, q.PR, q.aR, Pguess, e);
-            fPguess = e.fL + e.fR + q.du;
-            fpsum = e.fpL + e.fpR;
-        }
-    }
-    if (1.e6 * fabs(Pstar - Pguess) > 0.5 * (Pstar + Pguess) && fPguess > 0.)
-        return rs_brent(c, q.rhoL, q.PL, q.aL, q.rhoR, q.PR, q.aR, q.du, Pstar, Pguess, fPstar, fPguess);
-    return Pguess;
 }
 
 // star state at x/t = 0; returns +1 (right of the contact sampled) or -1 (left); Riemann.cpp:104-127 reads the flag
@@ -705,96 +743,141 @@ __global__ void __launch_bounds__(MLH_FACE_TILE) k_face_states(const Params p, d
 
 // ---------------------------------------------------------------------------------------------
 // K4b: one thread per staged record -- the Riemann class of the reference.
-// The root finder has two very different costs per face (Newton: 2-4 evaluations; Brent: ~10, taken whenever
-// the initial guess lies above the root, i.e. for about half of all faces), randomly mixed inside a warp.  So
-// each 128-face tile is regrouped between the solver stages through shared memory: Newton faces are handed to
-// the low threads of the block, Brent faces to the high threads, and at most one warp runs a mixed bag.
+// The number of root-finder iterations per face is strongly non-uniform (Newton 1-3, Brent 3-20 with a long
+// tail) and random inside a warp; run lane-per-face to completion, the warps were 28 % full (ncu,
+// profiles/r01b).  So the iteration state of a 128-face tile lives in shared memory and after EVERY
+// iteration the unfinished faces are re-compacted (ballot + prefix): round r runs ceil(U_r/32) full warps
+// instead of 4 mostly empty ones; Newton faces are listed before Brent faces so warps stay homogeneous.
 // ---------------------------------------------------------------------------------------------
-#define MLH_RS_FIELDS 11
+#define MLH_RS_FIELDS 14
+#ifndef MLH_K4B_BLOCKS_PER_SM
+#define MLH_K4B_BLOCKS_PER_SM 8
+#endif
 template <int D>
-__global__ void __launch_bounds__(MLH_FACE_TILE, 4) k_face_riemann(const Params p, double *__restrict__ stage, int c0, int cn, int cstride) {
+__device__ __forceinline__ void face_load(const double *rec, size_t fs, double *Wa, double *Wb, double *vF, double *A) {
+    using R = FaceRec<D>;
+#pragma unroll
+    for (int nu = 0; nu < D + 2; ++nu) {
+        Wa[nu] = rec[(R::WA + nu) * fs];
+        Wb[nu] = rec[(R::WB + nu) * fs];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        vF[k] = rec[(R::VF + k) * fs];
+        A[k] = rec[(R::AA + k) * fs];
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_riemann(const Params p, double *__restrict__ stage, int c0, int cn, int cstride) {
     constexpr int NW = D + 2;
     constexpr int T = MLH_FACE_TILE;
     using R = FaceRec<D>;
-    __shared__ double sh[MLH_RS_FIELDS][T]; // solver problem of face `slot`, SoA (conflict-free)
-    __shared__ int sh_item[T];              // work item -> face slot
-    __shared__ int sh_wcount[2][T / 32];
+    __shared__ double sh[MLH_RS_FIELDS][T]; // [0..6] problem, [7..13] iteration state of face `slot` (SoA: conflict-free)
+    __shared__ int sh_flags[T];             // method | mflag << 2 | vacuum << 3
+    __shared__ int sh_list[2][T];           // unfinished faces of the coming round, double buffered
+    __shared__ int sh_count[3];             // their number, triple buffered (reset one round ahead)
     const int tiles_per_slot = (cn + T - 1) / T;
     const int smax = (int)p.d.counters[3];
     const int ntiles = tiles_per_slot * smax;
     const size_t fs = (size_t)p.max_ni * cstride;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned below = (1u << lane) - 1u;
     bool vacuum = false;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int s = t / tiles_per_slot;
         const int il = (t - s * tiles_per_slot) * T + tid;
         const bool valid = il < cn && s < p.d.noi[c0 + (il < cn ? il : 0)] + p.d.noig[c0 + (il < cn ? il : 0)];
         double *rec = stage + (size_t)s * cstride + il;
-        double Wa[NW], Wb[NW], vF[D], A[D];
-        FaceFrame<D> fr;
-        RsProblem q;
-        double sgn = 0., rhoSol = 0., uSol = 0., PSol = 0.;
-        int flag = 0;
-        int path = 0; // 0: nothing to iterate, 1: Newton first, 2: straight to Brent
+        int my_method = RS_DONE;
+        // ---- stage A: rotate, sound speeds, initial guess, f(0), f(guess): the iteration state goes to shared memory.
+        // Nothing else is kept in registers across the rounds (stage C re-reads the L2-hot record), so that 8 blocks
+        // fit on an SM and the few warps that are busy in late rounds still hide the FP64 latencies.
         if (valid) {
-#pragma unroll
-            for (int nu = 0; nu < NW; ++nu) {
-                Wa[nu] = rec[(R::WA + nu) * fs];
-                Wb[nu] = rec[(R::WB + nu) * fs];
-            }
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                vF[k] = rec[(R::VF + k) * fs];
-                A[k] = rec[(R::AA + k) * fs];
-            }
-            sgn = rec[R::SG * fs];
+            double Wa[NW], Wb[NW], vF[D], A[D];
+            FaceFrame<D> fr;
+            face_load<D>(rec, fs, Wa, Wb, vF, A);
             face_rotate<D>(A, Wa, Wb, fr);
+            RsProblem q;
             // left = canonical particle a, right = b, along +A (Riemann.cpp:93-94)
             if (rs_setup(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], q)) {
-                path = (q.f0 * q.fPguess >= 0.) ? 1 : 2;
+                RsIter it;
+                rs_iter_begin(q, it);
+                my_method = it.method;
                 sh[0][tid] = q.rhoL; sh[1][tid] = q.PL; sh[2][tid] = q.aL;
-                sh[3][tid] = q.rhoR; sh[4][tid] = q.PR; sh[5][tid] = q.aR;
-                sh[6][tid] = q.du; sh[7][tid] = q.Pguess; sh[8][tid] = q.fPguess;
-                sh[9][tid] = q.f0; sh[10][tid] = q.fpsum;
+                sh[3][tid] = q.rhoR; sh[4][tid] = q.PR; sh[5][tid] = q.aR; sh[6][tid] = q.du;
+                sh[7][tid] = it.a; sh[8][tid] = it.b; sh[9][tid] = it.c; sh[10][tid] = it.d;
+                sh[11][tid] = it.fa; sh[12][tid] = it.fb; sh[13][tid] = it.fc;
+                sh_flags[tid] = it.method | (it.mflag << 2);
             } else {
+                sh_flags[tid] = 8; // vacuum generated or present: solved in stage C
+            }
+        }
+        // ---- stage B: iterate; the list of unfinished faces is rebuilt after every round (one barrier per round) ----
+        int my_face = tid; // the face this thread iterated last
+        if (tid == 0) {
+            sh_count[0] = 0;
+            sh_count[1] = 0;
+        }
+        __syncthreads();
+        for (int r = 0;; ++r) {
+            const int cur = r % 3;
+            const unsigned act = __ballot_sync(0xffffffffu, my_method != RS_DONE);
+            if (act) {
+                int base = 0;
+                if (lane == __ffs(act) - 1) base = atomicAdd(&sh_count[cur], __popc(act));
+                base = __shfl_sync(0xffffffffu, base, __ffs(act) - 1);
+                if (my_method != RS_DONE) sh_list[r & 1][base + __popc(act & below)] = my_face;
+            }
+            __syncthreads();
+            // counter of round r+2 (= of round r-1): every thread read it before arriving at this barrier
+            if (tid == 0) sh_count[(r + 2) % 3] = 0;
+            const int nU = sh_count[cur];
+            if (nU == 0) break; // uniform across the block
+            my_method = RS_DONE;
+            if (tid < nU) {
+                const int f = sh_list[r & 1][tid];
+                my_face = f;
+                RsIter it;
+                it.a = sh[7][f]; it.b = sh[8][f]; it.c = sh[9][f]; it.d = sh[10][f];
+                it.fa = sh[11][f]; it.fb = sh[12][f]; it.fc = sh[13][f];
+                const int fl = sh_flags[f];
+                it.method = fl & 3;
+                it.mflag = (fl >> 2) & 1;
+                const double trial = rs_iter_trial(it);
+                RsEval e;
+                const double rhoL = sh[0][f], PL = sh[1][f], aL = sh[2][f], rhoR = sh[3][f], PR = sh[4][f], aR = sh[5][f];
+                if (__any_sync(__activemask(), it.method == RS_NEWTON)) {
+                    rs_eval2<true>(p.rs, rhoL, PL, aL, rhoR, PR, aR, trial, e);
+                } else {
+                    rs_eval2<false>(p.rs, rhoL, PL, aL, rhoR, PR, aR, trial, e);
+                    e.fpL = e.fpR = 0.;
+                }
+                rs_iter_update(it, trial, e.fL + e.fR + sh[6][f], e.fpL + e.fpR);
+                sh[7][f] = it.a; sh[8][f] = it.b; sh[9][f] = it.c; sh[10][f] = it.d;
+                sh[11][f] = it.fa; sh[12][f] = it.fb; sh[13][f] = it.fc;
+                sh_flags[f] = it.method | (it.mflag << 2);
+                my_method = it.method;
+            }
+        }
+        // ---- stage C: star state at x/t = 0, rotation back, projection ----
+        if (valid) {
+            double Wa[NW], Wb[NW], vF[D], A[D], F[NW];
+            FaceFrame<D> fr;
+            face_load<D>(rec, fs, Wa, Wb, vF, A);
+            const double sgn = rec[R::SG * fs];
+            face_rotate<D>(A, Wa, Wb, fr);
+            double rhoSol, uSol, PSol;
+            int flag;
+            if (sh_flags[tid] & 8) {
                 flag = rs_solve_vacuum(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], &rhoSol, &uSol, &PSol);
                 vacuum = vacuum || flag == 0;
+            } else {
+                RsProblem q;
+                q.rhoL = sh[0][tid]; q.PL = sh[1][tid]; q.aL = sh[2][tid];
+                q.rhoR = sh[3][tid]; q.PR = sh[4][tid]; q.aR = sh[5][tid]; q.du = sh[6][tid];
+                flag = rs_sample(p.rs, q, Wa[2], Wb[2], sh[8][tid], &rhoSol, &uSol, &PSol);
             }
-        }
-        // ---- regroup: Newton items from thread 0 upwards, Brent items from thread T-1 downwards ----
-        const unsigned bN = __ballot_sync(0xffffffffu, path == 1), bB = __ballot_sync(0xffffffffu, path == 2);
-        if (lane == 0) {
-            sh_wcount[0][wid] = __popc(bN);
-            sh_wcount[1][wid] = __popc(bB);
-        }
-        __syncthreads();
-        int offN = 0, offB = 0, nN = 0, nB = 0;
-#pragma unroll
-        for (int w = 0; w < T / 32; ++w) {
-            if (w < wid) {
-                offN += sh_wcount[0][w];
-                offB += sh_wcount[1][w];
-            }
-            nN += sh_wcount[0][w];
-            nB += sh_wcount[1][w];
-        }
-        const unsigned below = (1u << lane) - 1u;
-        if (path == 1) sh_item[offN + __popc(bN & below)] = tid;
-        if (path == 2) sh_item[T - 1 - (offB + __popc(bB & below))] = tid;
-        __syncthreads();
-        if (tid < nN || tid >= T - nB) {
-            const int f = sh_item[tid];
-            RsProblem w;
-            w.rhoL = sh[0][f]; w.PL = sh[1][f]; w.aL = sh[2][f];
-            w.rhoR = sh[3][f]; w.PR = sh[4][f]; w.aR = sh[5][f];
-            w.du = sh[6][f]; w.Pguess = sh[7][f]; w.fPguess = sh[8][f];
-            w.f0 = sh[9][f]; w.fpsum = sh[10][f];
-            sh[7][f] = rs_root(p.rs, w); // P*
-        }
-        __syncthreads();
-        if (valid) {
-            if (path != 0) flag = rs_sample(p.rs, q, Wa[2], Wb[2], sh[7][tid], &rhoSol, &uSol, &PSol);
-            double F[NW];
             face_project<D>(p, flag, rhoSol, uSol, PSol, Wa, Wb, fr, vF, A, F);
 #pragma unroll
             for (int nu = 0; nu < NW; ++nu) rec[(R::FX + nu) * fs] = sgn * F[nu];
