@@ -9,14 +9,14 @@
 //              layers goes to the slab neighbours, together with the particles that drifted across the slab
 //              boundary (migration).  The search grid has cell edge >= h (Domain.cpp:10-22), so ONE halo
 //              layer per side is enough for every later pass.
-//   exchange 2 (after K3, = updateGhostState): omega, rho, P, c_s, B^-1 of the boundary layers.
-//   exchange 3 (after K3b, = updateGhostGradients): the limited gradients; dt: allreduce-min.
+//   exchange 2 (after K3, = updateGhostState): the packed record pk1 (x, v, rho, P, c_s, omega) of the boundary layers.
+//   exchange 3 (after K3b, = updateGhostGradients): the packed record pk2 (B^-1, limited gradients); dt: allreduce-min.
 //
 // Slabs are whole cell layers along the slowest-varying cell axis (y in 2D, z in 3D: cell id = iX + iY*cellsX
 // + iZ*cellsX*cellsY, Particles.cpp:298-302).  After the cell sort the local particle arrays are ordered
 // [lower halo layer | owned layers | upper halo layer] and, inside a layer, by (cell, original id) -- the SAME
-// order on the sending and on the receiving rank.  Exchanges 2 and 3 are therefore plain contiguous-range
-// ncclSend/ncclRecv of the SoA arrays, no packing, no index lists.  A face cut by a slab boundary is
+// order on the sending and on the receiving rank.  Exchanges 2 and 3 are therefore ONE contiguous-range
+// ncclSend/ncclRecv per side of the packed per-particle records, no packing kernel, no index lists.  A face cut by a slab boundary is
 // evaluated by both ranks from bit-identical inputs in the canonical orientation (quirk Q4, global original
 // ids), so no flux is exchanged and conservation holds to round-off.
 //
@@ -314,21 +314,22 @@ int mlh_halo_read_layout(mlh_ctx *c) {
 
 // Exchanges 2 and 3: refresh the halo ranges of the given SoA arrays from the neighbours' boundary
 // layers (contiguous ranges, identical order on both sides -- see the header comment).
-int mlh_halo_refresh(mlh_ctx *c, double *const *arrays, int narrays) {
+int mlh_halo_refresh(mlh_ctx *c, double *const *arrays, int narrays, int width) {
     Params &p = c->p;
     ncclComm_t comm = (ncclComm_t)c->nccl_comm;
     int dn, up;
     slab_neighbours(c, &dn, &up);
     cudaStream_t st = c->stream;
-    const int n_lo_halo = p.own_begin, n_hi_halo = p.n - p.own_end;
-    const int n_lo_layer = c->lo_layer_end - p.own_begin, n_hi_layer = p.own_end - c->hi_layer_begin;
+    const size_t w = (size_t)width; // doubles per particle in these arrays
+    const size_t n_lo_halo = p.own_begin * w, n_hi_halo = (size_t)(p.n - p.own_end) * w;
+    const size_t n_lo_layer = (size_t)(c->lo_layer_end - p.own_begin) * w, n_hi_layer = (size_t)(p.own_end - c->hi_layer_begin) * w;
     mlh_prof_begin(c, KID_HALO);
     MLH_NCCL_CHECK(c, g_nccl.GroupStart());
     for (int a = 0; a < narrays; ++a) {
         double *arr = arrays[a];
-        if (dn >= 0 && n_lo_layer) MLH_NCCL_CHECK(c, g_nccl.Send(arr + p.own_begin, n_lo_layer, ncclDouble, dn, comm, st));
-        if (up >= 0 && n_hi_halo) MLH_NCCL_CHECK(c, g_nccl.Recv(arr + p.own_end, n_hi_halo, ncclDouble, up, comm, st));
-        if (up >= 0 && n_hi_layer) MLH_NCCL_CHECK(c, g_nccl.Send(arr + c->hi_layer_begin, n_hi_layer, ncclDouble, up, comm, st));
+        if (dn >= 0 && n_lo_layer) MLH_NCCL_CHECK(c, g_nccl.Send(arr + p.own_begin * w, n_lo_layer, ncclDouble, dn, comm, st));
+        if (up >= 0 && n_hi_halo) MLH_NCCL_CHECK(c, g_nccl.Recv(arr + p.own_end * w, n_hi_halo, ncclDouble, up, comm, st));
+        if (up >= 0 && n_hi_layer) MLH_NCCL_CHECK(c, g_nccl.Send(arr + c->hi_layer_begin * w, n_hi_layer, ncclDouble, up, comm, st));
         if (dn >= 0 && n_lo_halo) MLH_NCCL_CHECK(c, g_nccl.Recv(arr, n_lo_halo, ncclDouble, dn, comm, st));
     }
     MLH_NCCL_CHECK(c, g_nccl.GroupEnd());

@@ -127,7 +127,21 @@ __global__ void __launch_bounds__(128) k_density_matrix(const Params p) {
     p.d.omega[i] = omg;
     p.d.rho[i] = rho;
     p.d.P[i] = P;
-    p.d.cs[i] = sqrt(__ddiv_rn(__dmul_rn(p.gamma, P), rho)); // Particles.cpp:1451
+    const double cs = sqrt(__ddiv_rn(__dmul_rn(p.gamma, P), rho)); // Particles.cpp:1451
+    p.d.cs[i] = cs;
+    {   // packed gather record for K3b / K4a
+        double rec[MLH_PK1(D)];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            rec[k] = xi[k];
+            rec[D + k] = p.d.v[k][i];
+        }
+        rec[2 * D] = rho;
+        rec[2 * D + 1] = P;
+        rec[2 * D + 2] = cs;
+        rec[2 * D + 3] = omg;
+        store_packed<MLH_PK1(D)>(p.d.pk1 + (size_t)i * MLH_PK1(D), rec);
+    }
     // E matrix
     double E[D * D];
 #pragma unroll

@@ -24,28 +24,42 @@ __device__ __forceinline__ double dot_seq(const double *a, const double *b) { //
     return res;
 }
 
+// neighbour record for list entry e: pk1 of particle j with the periodic image applied to the position
+template <int D, bool PER>
+__device__ __forceinline__ void load_neighbour(const Params &p, int e, double *nb) {
+    const int j = e & MLH_NNL_IDX_MASK;
+    load_packed<MLH_PK1(D)>(p.d.pk1 + (size_t)j * MLH_PK1(D), nb);
+    if (PER) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) nb[k] = image_coord(nb[k], (e >> (MLH_NNL_IDX_BITS + 2 * k)) & 3, p.grid.bmin[k], p.grid.bmax[k]);
+    }
+}
+
 template <int D, bool PER>
 __global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
     constexpr int NF = D + 2;
+    constexpr int PK1 = MLH_PK1(D);
     int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
     double dt_i = DBL_MAX;
     if (i < p.own_end) {
-        // field tables: rho, vx, vy, (vz), P  (order of MeshlessScheme.cpp:114-120 and Particles.cpp:1329-1335)
-        const double *fld[NF];
-        int fslot[NF];
-        fld[0] = p.d.rho; fslot[0] = 0;
+        // fields: rho, vx, vy, (vz), P  (order of MeshlessScheme.cpp:114-120 and Particles.cpp:1329-1335);
+        // field f of a packed record sits at pk1 index fidx(f)
+        int fslot[NF], fidx[NF];
+        fslot[0] = 0; fidx[0] = 2 * D;
 #pragma unroll
-        for (int k = 0; k < D; ++k) { fld[1 + k] = p.d.v[k]; fslot[1 + k] = 1 + k; }
-        fld[NF - 1] = p.d.P; fslot[NF - 1] = 4;
+        for (int k = 0; k < D; ++k) { fslot[1 + k] = 1 + k; fidx[1 + k] = D + k; }
+        fslot[NF - 1] = 4; fidx[NF - 1] = 2 * D + 1;
 
+        double own[PK1];
+        load_packed<PK1>(p.d.pk1 + (size_t)i * PK1, own);
         double xi[3], fi[NF], B[D * D];
 #pragma unroll
-        for (int k = 0; k < D; ++k) xi[k] = p.d.x[k][i];
+        for (int k = 0; k < D; ++k) xi[k] = own[k];
 #pragma unroll
-        for (int f = 0; f < NF; ++f) fi[f] = fld[f][i];
+        for (int f = 0; f < NF; ++f) fi[f] = own[fidx[f]];
 #pragma unroll
         for (int k = 0; k < D * D; ++k) B[k] = p.d.B[k][i];
-        const double omg = p.d.omega[i];
+        const double omg = own[2 * D + 3];
         const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
 
         double g[NF][D];
@@ -57,9 +71,15 @@ __global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
         // ---- sweep 1: gradients ----
         for (int s = 0; s < ntot; ++s) {
             const int e = p.d.nnl[(size_t)s * p.ncap + i];
-            const int j = e & MLH_NNL_IDX_MASK;
-            double d[3], r;
-            neighbour_geometry<D, PER>(p, xi, e, d, &r);
+            double nb[PK1];
+            load_neighbour<D, PER>(p, e, nb);
+            double d[3], sd[3];
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                d[k] = __dsub_rn(nb[k], xi[k]);
+                sd[k] = __dsub_rn(xi[k], nb[k]);
+            }
+            const double r = sqrt(dist_sqr_exact<D>(sd)); // Particles.cpp:1170-1175 / :2275-2280
             const double psij = __ddiv_rn(cubic_spline(r, p), omg);
             double pt[D];
 #pragma unroll
@@ -71,7 +91,7 @@ __global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
             }
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
-                const double df = __dsub_rn(fld[f][j], fi[f]);
+                const double df = __dsub_rn(nb[fidx[f]], fi[f]);
 #pragma unroll
                 for (int a = 0; a < D; ++a) g[f][a] = __dadd_rn(g[f][a], __dmul_rn(df, pt[a]));
             }
@@ -83,30 +103,31 @@ __global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
                 for (int a = 0; a < D; ++a) p.d.gpre[fslot[f] * 3 + a][i] = g[f][a];
         }
 
-        // ---- sweep 2: slope limiter extrema + signal velocity ----
-        if (p.slope_limiting) {
-            double maxNgb[NF], minNgb[NF], maxMid[NF], minMid[NF];
+        // ---- sweep 2: slope limiter extrema (all entries) + signal velocity (regular entries only, quirk Q7) ----
+        double maxNgb[NF], minNgb[NF], maxMid[NF], minMid[NF];
 #pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                maxNgb[f] = DBL_MIN; // quirk Q2: smallest positive normal, not -inf
-                minNgb[f] = DBL_MAX;
-                maxMid[f] = DBL_MIN;
-                minMid[f] = DBL_MAX;
-            }
-            for (int s = 0; s < ntot; ++s) {
-                const int e = p.d.nnl[(size_t)s * p.ncap + i];
-                const int j = e & MLH_NNL_IDX_MASK;
+        for (int f = 0; f < NF; ++f) {
+            maxNgb[f] = DBL_MIN; // quirk Q2: smallest positive normal, not -inf
+            minNgb[f] = DBL_MAX;
+            maxMid[f] = DBL_MIN;
+            minMid[f] = DBL_MAX;
+        }
+        double vSig = DBL_MIN; // quirk Q2
+        const double ci = own[2 * D + 2];
+        for (int s = 0; s < ntot; ++s) {
+            const int e = p.d.nnl[(size_t)s * p.ncap + i];
+            double nb[PK1];
+            load_neighbour<D, PER>(p, e, nb);
+            if (p.slope_limiting) {
                 double xijxi[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    double xj = p.d.x[k][j];
-                    if (PER) xj = image_coord(xj, (e >> (MLH_NNL_IDX_BITS + 2 * k)) & 3, p.grid.bmin[k], p.grid.bmax[k]);
-                    const double xij = __ddiv_rn(__dadd_rn(xi[k], xj), 2.); // FIRST_ORDER_QUAD_POINT, :1355-1356
+                    const double xij = __ddiv_rn(__dadd_rn(xi[k], nb[k]), 2.); // FIRST_ORDER_QUAD_POINT, :1355-1356
                     xijxi[k] = __dsub_rn(xij, xi[k]);
                 }
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
-                    const double fj = fld[f][j];
+                    const double fj = nb[fidx[f]];
                     if (maxNgb[f] < fj) maxNgb[f] = fj;
                     if (minNgb[f] > fj) minNgb[f] = fj;
                     const double fij = __dadd_rn(fi[f], dot_seq<D>(g[f], xijxi));
@@ -114,6 +135,20 @@ __global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
                     if (minMid[f] > fij) minMid[f] = fij;
                 }
             }
+            if (s < nreg) { // compGlobalTimestep, Particles.cpp:1446-1485
+                double xij[D], vij[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    xij[k] = __dsub_rn(xi[k], nb[k]);
+                    vij[k] = __dsub_rn(own[D + k], nb[D + k]);
+                }
+                double vijxij = __ddiv_rn(dot_seq<D>(vij, xij), sqrt(dot_seq<D>(xij, xij)));
+                vijxij = vijxij < 0. ? vijxij : 0.;
+                const double vSig_i = __dsub_rn(__dadd_rn(ci, nb[2 * D + 2]), vijxij);
+                vSig = vSig_i > vSig ? vSig_i : vSig;
+            }
+        }
+        if (p.slope_limiting) {
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 const double alphaMax = q1_abs(__ddiv_rn(__dsub_rn(maxNgb[f], fi[f]), __dsub_rn(maxMid[f], fi[f])), p.abs_mode);
@@ -131,26 +166,17 @@ __global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
         for (int f = 0; f < NF; ++f)
 #pragma unroll
             for (int a = 0; a < D; ++a) p.d.g[fslot[f] * 3 + a][i] = g[f][a];
-
-        // ---- CFL: regular neighbours only (quirk Q7), vSig starts at DBL_MIN (quirk Q2) ----
-        double vSig = DBL_MIN;
-        const double ci = p.d.cs[i];
-        double vi[D];
+        {   // packed record for K4a: Binv, then gradients in W order rho, P, vx, vy(, vz)
+            double rec[MLH_PK2(D)];
 #pragma unroll
-        for (int k = 0; k < D; ++k) vi[k] = p.d.v[k][i];
-        for (int s = 0; s < nreg; ++s) {
-            const int j = p.d.nnl[(size_t)s * p.ncap + i];
-            const double cj = p.d.cs[j];
-            double xij[D], vij[D];
+            for (int k = 0; k < D * D; ++k) rec[k] = B[k];
 #pragma unroll
-            for (int k = 0; k < D; ++k) {
-                xij[k] = __dsub_rn(xi[k], p.d.x[k][j]);
-                vij[k] = __dsub_rn(vi[k], p.d.v[k][j]);
+            for (int nu = 0; nu < NF; ++nu) {
+                const int f = nu == 0 ? 0 : (nu == 1 ? NF - 1 : nu - 1);
+#pragma unroll
+                for (int a = 0; a < D; ++a) rec[D * D + nu * D + a] = g[f][a];
             }
-            double vijxij = __ddiv_rn(dot_seq<D>(vij, xij), sqrt(dot_seq<D>(xij, xij)));
-            vijxij = vijxij < 0. ? vijxij : 0.;
-            const double vSig_i = __dsub_rn(__dadd_rn(ci, cj), vijxij);
-            vSig = vSig_i > vSig ? vSig_i : vSig;
+            store_packed<MLH_PK2(D)>(p.d.pk2 + (size_t)i * MLH_PK2(D), rec);
         }
         dt_i = __ddiv_rn(__dmul_rn(p.cfl, p.h), vSig);
         if (!(dt_i < DBL_MAX)) dt_i = DBL_MAX; // `dt < dt_` never selects NaN / inf

@@ -537,9 +537,13 @@ template <int D> struct FaceRec {
 // ---------------------------------------------------------------------------------------------
 // K4a: one thread per (slot, particle)
 // ---------------------------------------------------------------------------------------------
+#ifndef MLH_K4A_BLOCKS_PER_SM
+#define MLH_K4A_BLOCKS_PER_SM 2
+#endif
 template <int D, bool PER>
-__global__ void __launch_bounds__(MLH_FACE_TILE) k_face_states(const Params p, double *__restrict__ stage, int c0, int cn, int cstride) {
+__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_states(const Params p, double *__restrict__ stage, int c0, int cn, int cstride) {
     constexpr int NW = D + 2;
+    constexpr int PK1 = MLH_PK1(D), PK2 = MLH_PK2(D);
     using R = FaceRec<D>;
     const int tiles_per_slot = (cn + MLH_FACE_TILE - 1) / MLH_FACE_TILE;
     const int smax = (int)p.d.counters[3]; // max list length (K2)
@@ -560,16 +564,12 @@ __global__ void __launch_bounds__(MLH_FACE_TILE) k_face_states(const Params p, d
         // canonical orientation: the endpoint with the lower ORIGINAL index plays "i" (Particles.cpp:1841,1889)
         const bool canon = !(idn < ids);
         const int ia = canon ? i : j, ib = canon ? j : i; // a = canonical endpoint, b = the other
-        double xa[D], xb[D], va[D], vb[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            xa[k] = p.d.x[k][ia];
-            xb[k] = p.d.x[k][ib];
-            va[k] = p.d.v[k][ia];
-            vb[k] = p.d.v[k][ib];
-        }
-        const double rhoa = p.d.rho[ia], rhob = p.d.rho[ib], Pa = p.d.P[ia], Pb = p.d.P[ib];
-        const double omga = p.d.omega[ia], omgb = p.d.omega[ib];
+        double A1[PK1], B1[PK1]; // packed records: x, v, rho, P, cs, omega
+        load_packed<PK1>(p.d.pk1 + (size_t)ia * PK1, A1);
+        load_packed<PK1>(p.d.pk1 + (size_t)ib * PK1, B1);
+        const double *xa = A1, *xb = B1, *va = A1 + D, *vb = B1 + D;
+        const double rhoa = A1[2 * D], rhob = B1[2 * D], Pa = A1[2 * D + 1], Pb = B1[2 * D + 1];
+        const double omga = A1[2 * D + 3], omgb = B1[2 * D + 3];
 
         // ---- geometry: b's image as a sees it, a's image as b sees it (identity for regular pairs) ----
         double xbi[D], xai[D];
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE) k_face_states(const Params p, d
         }
 
         // ---- effective face A_ab = psi~_b(x_a)/omega_a - psi~_a(x_b)/omega_b (Particles.cpp:1299-1302, :2525-2528) ----
-        double A[D];
+        double A[D], ga[NW][D], gb[NW][D];
         {
             double s1[3], s2[3], d1[D], d2[D];
 #pragma unroll
@@ -620,27 +620,29 @@ __global__ void __launch_bounds__(MLH_FACE_TILE) k_face_states(const Params p, d
             const double w1 = cubic_spline(r1, p);
             const double w2 = (PER && code != 0) ? cubic_spline(r2, p) : w1;
             const double psi1 = w1 / omga, psi2 = w2 / omgb;
+            double A2[PK2], B2[PK2]; // packed records: Binv, limited gradients (W order)
+            load_packed<PK2>(p.d.pk2 + (size_t)ia * PK2, A2);
+            load_packed<PK2>(p.d.pk2 + (size_t)ib * PK2, B2);
 #pragma unroll
             for (int al = 0; al < D; ++al) {
                 double t1 = 0., t2 = 0.;
 #pragma unroll
                 for (int be = 0; be < D; ++be) {
-                    t1 += p.d.B[D * al + be][ia] * d1[be] * psi1;
-                    t2 += p.d.B[D * al + be][ib] * d2[be] * psi2;
+                    t1 += A2[D * al + be] * d1[be] * psi1;
+                    t2 += B2[D * al + be] * d2[be] * psi2;
                 }
                 A[al] = 1. / omga * t1 - 1. / omgb * t2;
             }
+#pragma unroll
+            for (int nu = 0; nu < NW; ++nu)
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    ga[nu][k] = A2[D * D + nu * D + k];
+                    gb[nu][k] = B2[D * D + nu * D + k];
+                }
         }
 
         // ---- boosted, reconstructed, predicted states (Particles.cpp:1498-1721; ghosts :2546-2672) ----
-        double ga[NW][D], gb[NW][D];
-#pragma unroll
-        for (int nu = 0; nu < NW; ++nu)
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                ga[nu][k] = p.d.g[w2f(nu) * 3 + k][ia];
-                gb[nu][k] = p.d.g[w2f(nu) * 3 + k][ib];
-            }
         double xjxi[3], xijxi[D], xijxj[D], vF[D], Wa[NW], Wb[NW];
         xjxi[2] = 0.; // quirk Q13 (ZERO_Z): never written in the first-order 3D branch
 #pragma unroll

@@ -80,6 +80,8 @@ static void carve_pool(mlh_ctx *c, Carver &cv) {
         if (f == 3 && D == 2) continue;
         for (int a = 0; a < D; ++a) d.g[f * 3 + a] = cv.take<double>(n);
     }
+    d.pk1 = cv.take<double>(n * (size_t)MLH_PK1(D));
+    d.pk2 = cv.take<double>(n * (size_t)MLH_PK2(D));
     d.id = cv.take<int>(n); d.cid = cv.take<int>(n); d.cell = cv.take<int>(n);
     d.noi = cv.take<int>(n); d.noig = cv.take<int>(n);
     d.ckey = cv.take<int>(n); d.crank = cv.take<int>(n); d.perm = cv.take<int>(n);
@@ -515,11 +517,8 @@ int mlh_density_matrix(mlh_ctx *c) {
     int rc = mlh_launch_density(c);
     if (rc == MLH_OK && c->cfg.nranks > 1) { // exchange 2 (updateGhostState point, MeshlessScheme.cpp:109)
         Params &p = c->p;
-        double *arr[16];
-        int na = 0;
-        arr[na++] = p.d.omega; arr[na++] = p.d.rho; arr[na++] = p.d.P; arr[na++] = p.d.cs;
-        for (int k = 0; k < p.D * p.D; ++k) arr[na++] = p.d.B[k];
-        rc = mlh_halo_refresh(c, arr, na);
+        double *arr[1] = {p.d.pk1}; // x, v, rho, P, cs, omega of the boundary layers, one contiguous range per side
+        rc = mlh_halo_refresh(c, arr, 1, MLH_PK1(p.D));
     }
     if (rc == MLH_OK) c->phase = 3;
     return rc;
@@ -534,13 +533,8 @@ int mlh_gradients_limit(mlh_ctx *c) {
     int rc = mlh_launch_gradient(c);
     if (rc == MLH_OK && c->cfg.nranks > 1) { // exchange 3 (updateGhostGradients point, :129) + global dt
         Params &p = c->p;
-        double *arr[16];
-        int na = 0;
-        for (int f = 0; f < 5; ++f) {
-            if (f == 3 && p.D == 2) continue;
-            for (int a = 0; a < p.D; ++a) arr[na++] = p.d.g[f * 3 + a];
-        }
-        rc = mlh_halo_refresh(c, arr, na);
+        double *arr[1] = {p.d.pk2}; // Binv + limited gradients of the boundary layers
+        rc = mlh_halo_refresh(c, arr, 1, MLH_PK2(p.D));
         if (rc == MLH_OK) rc = mlh_comm_min_dt(c);
     }
     if (rc == MLH_OK) c->phase = 4;

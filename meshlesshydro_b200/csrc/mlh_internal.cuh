@@ -18,6 +18,8 @@
 #include "../../include/mlh_gpu.h"
 
 #define MLH_MAX_D 3
+#define MLH_PK1(D) (2 * (D) + 4)
+#define MLH_PK2(D) ((D) * (D) + ((D) + 2) * (D))
 #define MLH_NNL_IDX_BITS 26
 #define MLH_NNL_IDX_MASK ((1 << MLH_NNL_IDX_BITS) - 1)
 
@@ -42,6 +44,11 @@ struct DevPtrs {
     double *B[9];   // Binv row-major as used by the reference (Particles.cpp:1249)
     double *g[15];  // gradients: field f in {0 rho,1 vx,2 vy,3 vz,4 P}; component a -> g[f*3+a]
     int *id, *cell, *noi, *noig, *nnl;
+    // packed (AoS) gather records of the SRT set -- what a neighbour visit needs, contiguous per particle so that a
+    // gather costs 3 (pk1) + 6 (pk2) 32-byte sectors instead of one sector per scalar array:
+    //   pk1[i*PK1 ..] = x[D], v[D], rho, P, cs, omega          (written by K3;  PK1 = 2D+4)
+    //   pk2[i*PK2 ..] = Binv[D*D] row-major, grad[(D+2)][D] in W order rho,P,vx,vy(,vz)   (written by K3b; PK2 = D*D+(D+2)*D)
+    double *pk1, *pk2;
     // CUR set
     double *cx[3], *cv[3], *cm, *cu;
     int *cid;
@@ -139,6 +146,26 @@ __device__ __forceinline__ double q1_abs(double v, int mode) {
     return (double)k;
 }
 
+// 16-byte vector loads/stores of a packed record (PKn is even and the arrays are 256-byte aligned)
+template <int N>
+__device__ __forceinline__ void load_packed(const double *__restrict__ src, double *dst) {
+    static_assert(N % 2 == 0, "packed records hold an even number of doubles");
+    const double2 *s2 = reinterpret_cast<const double2 *>(src);
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+        const double2 v = __ldg(s2 + k);
+        dst[2 * k] = v.x;
+        dst[2 * k + 1] = v.y;
+    }
+}
+template <int N>
+__device__ __forceinline__ void store_packed(double *dst, const double *src) {
+    static_assert(N % 2 == 0, "packed records hold an even number of doubles");
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) d2[k] = make_double2(src[2 * k], src[2 * k + 1]);
+}
+
 // displacement (neighbour - self) and distance for list entry e of particle i, the way the reference
 // evaluates it for a regular neighbour (Particles.cpp:1170-1175) or a ghost (:2275-2280)
 template <int D, bool PER>
@@ -221,7 +248,7 @@ void mlh_comm_destroy(mlh_ctx *c);
 int mlh_comm_bbox(mlh_ctx *c);
 int mlh_halo_exchange_particles(mlh_ctx *c);
 int mlh_halo_read_layout(mlh_ctx *c);
-int mlh_halo_refresh(mlh_ctx *c, double *const *arrays, int narrays);
+int mlh_halo_refresh(mlh_ctx *c, double *const *arrays, int narrays, int width);
 int mlh_comm_min_dt(mlh_ctx *c);
 int mlh_comm_sum(mlh_ctx *c, double *dev, int n);
 int mlh_launch_unpermute_f64(mlh_ctx *c, const double *src, const int *ids, double *dst, int n, int comps, int stride); // k5_reduce.cu
