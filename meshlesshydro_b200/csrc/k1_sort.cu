@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_sums(int *tile_sums, int ntiles
         if (threadIdx.x == 0) carry += total;
         __syncthreads();
     }
+    if (threadIdx.x == 0) tile_sums[ntiles] = carry; // grand total
 }
 
 __global__ void __launch_bounds__(SCAN_T) k_scan_add(int *out, const int *tile_sums, int n, int total_slot, int total_value) {
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_add(int *out, const int *tile_s
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k)
         if (base + k < n) out[base + k] += add;
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[total_slot] = total_value;
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[total_slot] = total_value >= 0 ? total_value : tile_sums[gridDim.x];
 }
 
 __global__ void __launch_bounds__(256) k_scatter_perm(const Params p) {
@@ -176,6 +177,16 @@ __global__ void __launch_bounds__(256) k_gather_sorted(const Params p) {
 }
 
 } // namespace
+
+int mlh_exclusive_scan(mlh_ctx *c, const int *in, int *out, int *tmp, int n) {
+    cudaStream_t st = c->stream;
+    const int ntiles = mlh_blocks(n, SCAN_TILE);
+    k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(in, out, tmp, n);
+    k_scan_sums<<<1, SCAN_T, 0, st>>>(tmp, ntiles);       // afterwards tmp[ntiles] = grand total
+    k_scan_add<<<ntiles, SCAN_T, 0, st>>>(out, tmp, n, n, -1);
+    c->launches += 3;
+    return MLH_OK;
+}
 
 int mlh_launch_sort(mlh_ctx *c) {
     Params &p = c->p;

@@ -165,6 +165,38 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
     }
     p.d.noig[i] = ng;
     if (overflow) atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
+    // ---- face ownership: the flux pass (k4_flux.cu) evaluates every pair once, from its owner, and both endpoints
+    // gather +-F.  Owner = the endpoint with the lower ORIGINAL index (the one that solves the face in the reference,
+    // Particles.cpp:1841,1889); always this particle when the partner has no list on this rank (halo of another slab)
+    // or does not list the pair (one-sided periodic pair, quirk Q9).
+    {
+        const int ntot = nreg + ng;
+        const int idi = p.d.id[i];
+        int nown = 0;
+        for (int s = 0; s < ntot; ++s) {
+            const int e = p.d.nnl[(size_t)s * p.ncap + i];
+            const int j = e & MLH_NNL_IDX_MASK;
+            const bool canon = !(p.d.id[j] < idi);
+            bool listed = true; // does j list this pair too?  (the test of pass B from j's side; exact for regular pairs)
+            if (PER && s >= nreg && !p.symmetric_seam) {
+                const int cview = reverse_code((int)((unsigned)e >> MLH_NNL_IDX_BITS)); // image of i as j sees it
+                double dd[3];
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const int ck = (cview >> (2 * k)) & 3;
+                    listed = listed && image_exists(xi[k], ck, g.bmin[k], g.bmax[k], p.h);
+                    dd[k] = __dsub_rn(image_coord(xi[k], ck, g.bmin[k], g.bmax[k]), p.d.x[k][j]);
+                }
+                listed = listed && (dist_sqr_exact<D>(dd) < p.hSqr);
+                if (!listed) atomicAdd(&p.d.counters[0], 1u); // one-sided pair (statistics for the parity harness)
+            }
+            const bool own = canon || !listed || j < p.own_begin || j >= p.own_end;
+            p.d.nnlT[(size_t)i * p.max_ni + s] = e;
+            p.d.fmap[(size_t)s * p.ncap + i] = own ? (((unsigned)nown << 2) | 2u | (canon ? 0u : 1u)) : 0u;
+            nown += own ? 1 : 0;
+        }
+        p.d.nown[i] = nown;
+    }
     // longest list of this step: bounds the slot loop of the persistent face kernels (k4_flux.cu)
     {
         const unsigned am = __activemask();

@@ -8,28 +8,33 @@
 //   Helper::rotationMatrix2D/3D         Helper.cpp:39-77, RiemannSolver::solve (restated, see oracle/riemann_exact.h)
 //   Particles::collectFluxes            :1913-2011, Particles::updateStateAndPosition :2013-2110
 //
-// Three kernels per particle chunk, one thread per FACE EVALUATION in the first two:
-//   k_face_states  (K4a) thread (slot s, particle i): A_ij, boosted + reconstructed + limited + predicted states
-//                        of both endpoints -> face record (4D+5 doubles) in a slot-major staging buffer.
-//                        Gather-bound (both endpoint bundles come through L1/L2), needs ~200 registers.
-//   k_face_riemann (K4b) thread per record: rotate into the face frame, exact Riemann solve, rotate back,
-//                        project -> +-F (D+2 doubles).  Pure FP64; ~100 registers so 5 warps per scheduler
-//                        hide the DFMA/MUFU latencies; its code (one noinline pow, Newton loop with cached
-//                        f/f') stays inside the instruction cache.  [The first version fused all of this
-//                        into one 255-register, 145 KB kernel: ncu showed 56 % of the warp stalls were
-//                        instruction fetches and 14 % FP64-pipe use -- profiles/r01_k4_fused_*.]
-//   k_flux_sum_update (K4c/K5) thread per particle: sum of the slot fluxes in list order, conserved update, drift.
+// Every pair (i,j) of the neighbour lists is ONE face.  The reference (ENFORCE_FLUX_SYM, quirk Q4) solves a face
+// once, from the endpoint with the LOWER ORIGINAL index, and hands the other endpoint the exact negation
+// (Particles.cpp:1838-1858, ghosts :1886-1907).  Same here: K2 marks the owner of every list slot, k_face_index
+// numbers the owned slots (exclusive scan of the per-particle counts) and resolves, for every non-owned slot, the
+// face index its partner assigned -- so each face is evaluated once and both endpoints GATHER +-F in their own list
+// order.  No atomics, bit-reproducible, and total mass / momentum / energy are conserved to round-off (both ends
+// add the same bits with opposite sign).  Faces whose partner has no list on this rank (halo particle of another
+// slab) or does not list the pair (one-sided periodic pair, quirk Q9) are owned by the listing side; two ranks then
+// evaluate a cut face redundantly with identical operands, so conservation holds across slabs without a flux exchange.
 //
-// Gather-side and atomic-free: every face (i,j) is evaluated from BOTH endpoints.  The reference
-// (ENFORCE_FLUX_SYM, quirk Q4) solves a face once, from the endpoint with the LOWER ORIGINAL index, and gives
-// the other endpoint the exact negation; here both endpoint threads evaluate that same canonical orientation
-// (operands swapped with selects) and the non-canonical one negates.  Both add bit-identical +-F, so total
-// mass, momentum and energy are conserved to round-off without any exchange -- also across slab boundaries.
+// Kernels (one thread per FACE in the first three):
+//   k_face_index      thread per particle: face list fa/fe (owner, list entry) + slot -> face map (fmap).
+//   k_face_states (K4a)  A_ij, boosted + reconstructed + limited + predicted states of both endpoints -> face
+//                        record (4D+4 doubles) in a field-major staging buffer.  Gather-bound; consecutive faces
+//                        share their owner, so half of the gather is a warp broadcast.
+//   k_face_riemann (K4b) rotate into the face frame, exact Riemann solve, rotate back, project -> F (D+2
+//                        doubles, canonical orientation) into the per-face flux array.  Pure FP64; the iteration
+//                        state lives in shared memory and unfinished faces are regrouped after every iteration.
+//                        [The first version fused everything into one 255-register, 145 KB kernel: ncu showed 56 %
+//                        of the warp stalls were instruction fetches and 14 % FP64-pipe use -- profiles/r01a_*.]
+//   k_flux_sum_update (K4c/K5) thread per particle: signed sum of the faces of its slots in list order,
+//                        conserved update, drift.
 // The per-slot buffers of the reference (psijTilde, Aij, WijL/R, Fij, vFrame for ALL particles, ~100 kB per
-// particle, Particles.h:201-229) are replaced by the chunk-sized staging buffer.
+// particle, Particles.h:201-229) are replaced by the chunk-sized staging buffer and 32/48 B of flux per face.
 //
-// Roofline: K4b is FP64-pipe bound; K4a/K4c are L2/HBM gather passes (staging traffic (5D+7)*8 B per face
-// evaluation, written once and read once).
+// Roofline: K4b is FP64-pipe bound; K4a/K4c are L2/HBM gather passes (staging traffic (4D+4)*8 B per face,
+// written once and read once).
 #include "mlh_internal.cuh"
 #include <cfloat>
 
@@ -49,6 +54,26 @@ __device__ __forceinline__ double rs_min(double a, double b) { return (b < a) ? 
 
 __device__ __noinline__ double mlh_pow(double x, double y) { return x == 0. ? 0. : exp(y * log(x)); }
 
+// x^((gamma-1)/(2 gamma)), the one power the root finder evaluates every iteration.  For gamma = 5/3 and 7/5 the
+// exponent is 1/5 resp. 1/7: z = x^(-1/n) by two division-free Newton steps z <- z + z (1 - x z^n)/n from a
+// single-precision seed (relative error 5e-7 -> 7e-13 -> 2e-24, i.e. rounding-limited), then x^(1/n) = x z^(n-1).
+// ~20 FP64 instructions instead of ~130 for exp(y log x); x = 1 gives exactly 1 (as pow does), which keeps
+// f(P) = 0 exact on faces between identical states.  Other gamma, and x outside [1e-30, 1e30], take the generic path.
+__device__ __forceinline__ double rs_root_pow(const RsConsts &c, double x) {
+    const int n = c.root_n;
+    if (n == 0 || !(x > 1e-30 && x < 1e30)) return mlh_pow(x, c.gm1d2g);
+    const double rn = c.gm1d2g; // 1/n
+    double z = (double)exp2f(-__log2f((float)x) * (float)rn);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double z2 = z * z, z4 = z2 * z2;
+        const double zn = (n == 5) ? z4 * z : z4 * z2 * z;
+        z = fma(z, fma(-x, zn, 1.) * rn, z);
+    }
+    const double z2 = z * z, z4 = z2 * z2;
+    return x * ((n == 5) ? z4 : z4 * z2);
+}
+
 // f_K(Ps) and (optionally) f_K'(Ps) of BOTH sides, Toro eqs. 4.6/4.7/4.37.  In smooth flow P* lies between
 // PL and PR, i.e. every face has one (weak) shock side and one rarefaction side -- but WHICH side differs from
 // lane to lane.  Evaluating "left, then right" would run the pow and the sqrt twice with half-empty warps;
@@ -65,18 +90,19 @@ __device__ __forceinline__ void rs_eval2(const RsConsts &c, double rhoL, double 
     if (!shL || !shR) {
         const bool firstL = !shL;
         const double r1 = Ps / (firstL ? PL : PR);
-        const double w1 = mlh_pow(r1, c.gm1d2g);
+        const double w1 = rs_root_pow(c, r1);
         if (firstL) { wL = w1; rL = r1; } else { wR = w1; rR = r1; }
         if (!shL && !shR) {
             rR = Ps / PR;
-            wR = mlh_pow(rR, c.gm1d2g);
+            wR = rs_root_pow(c, rR);
         }
     }
     if (shL || shR) {
         const bool firstL = shL;
-        const double q1 = sqrt((c.tdgp1 / (firstL ? rhoL : rhoR)) / (Ps + c.gm1dgp1 * (firstL ? PL : PR)));
+        // sqrt(A_K / (Ps + B_K)) = sqrt(2/(g+1)) / sqrt(rho_K (Ps + B_K)): one rsqrt instead of two divisions and a sqrt
+        const double q1 = c.sqrt_tdgp1 * rsqrt((firstL ? rhoL : rhoR) * (Ps + c.gm1dgp1 * (firstL ? PL : PR)));
         if (firstL) qL = q1; else qR = q1;
-        if (shL && shR) qR = sqrt((c.tdgp1 / rhoR) / (Ps + c.gm1dgp1 * PR));
+        if (shL && shR) qR = c.sqrt_tdgp1 * rsqrt(rhoR * (Ps + c.gm1dgp1 * PR));
     }
     e.wL = wL;
     e.wR = wR;
@@ -524,40 +550,105 @@ __global__ void k_select_dt(const Params p, double dt_fixed, double dt_max) {
 // W component nu -> gradient field slot: W = [rho, P, vx, vy, vz], slots rho 0, vx 1, vy 2, vz 3, P 4
 __device__ __forceinline__ int w2f(int nu) { return nu == 0 ? 0 : (nu == 1 ? 4 : nu - 1); }
 
-// staging record of one face evaluation: Wa[NW], Wb[NW], vF[D], A[D], sign -> 4D+5 doubles, then F[NW]
+// staging record of one face: Wa[NW], Wb[NW], vF[D], A[D] -> 4D+4 doubles, field-major (field k of face f of the
+// chunk at stage[k * cstride + f]) so that both K4a's stores and K4b's loads are coalesced
 template <int D> struct FaceRec {
     static constexpr int NW = D + 2;
-    static constexpr int WA = 0, WB = NW, VF = 2 * NW, AA = 2 * NW + D, SG = 2 * NW + 2 * D, NREC = 2 * NW + 2 * D + 1;
-    static constexpr int FX = NREC, NTOT = NREC + NW;
+    static constexpr int WA = 0, WB = NW, VF = 2 * NW, AA = 2 * NW + D, NREC = 2 * NW + 2 * D;
 };
 
-// tile t of a chunk: slot s = t / tiles_per_slot, particles [c0 + 128 (t % tiles_per_slot), +128)
 #define MLH_FACE_TILE 128
+
+// ---------------------------------------------------------------------------------------------
+// face list: fa/fe for the owned slots, global face index for the others
+// ---------------------------------------------------------------------------------------------
+// One lane per particle; the search for a non-owned slot's face -- "where am I in my partner's list?" -- is done by
+// the whole warp: the partner's row of the particle-major list copy is read with one coalesced request and matched
+// with a ballot (a per-lane scan of the slot-major lists was L1-tag bound: 9 sectors per request, profiles/r01h).
+template <bool PER>
+__global__ void __launch_bounds__(128) k_face_index(const Params p) {
+    const int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool active = i < p.own_end;
+    const int nreg = active ? p.d.noi[i] : 0, ntot = active ? nreg + p.d.noig[i] : 0;
+    const int fs = active ? p.d.face_start[i] : 0;
+    const int smax = __reduce_max_sync(0xffffffffu, ntot);
+    bool over = false;
+    for (int s = 0; s < smax; ++s) {
+        const bool has = s < ntot;
+        const size_t at = (size_t)s * p.ncap + (active ? i : p.own_begin);
+        const unsigned v = has ? p.d.fmap[at] : 2u;
+        const int e = has ? p.d.nnl[at] : 0;
+        if (has && (v & 2u)) {
+            const int f = fs + (int)(v >> 2);
+            if (f < p.fcap) {
+                p.d.fa[f] = i;
+                p.d.fe[f] = e;
+            } else {
+                over = true;
+            }
+        }
+        // the partner owns the face: find this particle in ITS list (entry = i | reversed image code)
+        const bool need = has && !(v & 2u);
+        const int j = e & MLH_NNL_IDX_MASK;
+        const int want = i | (PER ? (reverse_code((int)((unsigned)e >> MLH_NNL_IDX_BITS)) << MLH_NNL_IDX_BITS) : 0);
+        int t0 = 0, tend = 0;
+        if (need) {
+            const int nrj = p.d.noi[j];
+            const bool ghost = PER && s >= nreg;
+            t0 = ghost ? nrj : 0;
+            tend = ghost ? nrj + p.d.noig[j] : nrj;
+        }
+        int found = -1;
+        unsigned m = __ballot_sync(0xffffffffu, need);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int jb = __shfl_sync(0xffffffffu, j, b), wb = __shfl_sync(0xffffffffu, want, b);
+            const int tb = __shfl_sync(0xffffffffu, t0, b), te = __shfl_sync(0xffffffffu, tend, b);
+            const int *row = p.d.nnlT + (size_t)jb * p.max_ni;
+            for (int base = tb; base < te; base += 32) {
+                const int t = base + lane;
+                const bool ok = t < te && __ldg(row + t) == wb;
+                const unsigned hit = __ballot_sync(0xffffffffu, ok);
+                if (hit) {
+                    if (lane == b) found = base + __ffs(hit) - 1;
+                    break;
+                }
+            }
+        }
+        if (need) {
+            unsigned res = MLH_FMAP_SKIP;
+            if (found >= 0) {
+                const unsigned vj = p.d.fmap[(size_t)found * p.ncap + j]; // owned by j: rank << 2 | 2 | sign
+                res = ((unsigned)(p.d.face_start[j] + (int)(vj >> 2)) << 2) | 1u;
+            } else {
+                over = true; // j's list overflowed (MLH_F_MAX_INTERACTIONS is raised by K2 as well)
+            }
+            p.d.fmap[at] = res;
+        }
+    }
+    if (over) atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
+}
 
 // ---------------------------------------------------------------------------------------------
 // K4a: one thread per (slot, particle)
 // ---------------------------------------------------------------------------------------------
 #ifndef MLH_K4A_BLOCKS_PER_SM
-#define MLH_K4A_BLOCKS_PER_SM 2
+#define MLH_K4A_BLOCKS_PER_SM 4
 #endif
 template <int D, bool PER>
-__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_states(const Params p, double *__restrict__ stage, int c0, int cn, int cstride) {
+__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_states(const Params p, double *__restrict__ stage, int f0, int cstride) {
     constexpr int NW = D + 2;
     constexpr int PK1 = MLH_PK1(D), PK2 = MLH_PK2(D);
     using R = FaceRec<D>;
-    const int tiles_per_slot = (cn + MLH_FACE_TILE - 1) / MLH_FACE_TILE;
-    const int smax = (int)p.d.counters[3]; // max list length (K2)
-    const int ntiles = tiles_per_slot * smax;
+    const int nfaces = min(p.d.face_start[p.own_end], p.fcap);
+    const int f1 = min(nfaces, f0 + cstride);
     const double dt = *p.d.dt_used;
     const double gamma = p.gamma;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int s = t / tiles_per_slot;
-        const int il = (t - s * tiles_per_slot) * MLH_FACE_TILE + threadIdx.x; // index inside the chunk
-        if (il >= cn) continue;
-        const int i = c0 + il;
-        const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
-        if (s >= ntot) continue;
-        const int e = p.d.nnl[(size_t)s * p.ncap + i];
+    for (int f = f0 + blockIdx.x * MLH_FACE_TILE + threadIdx.x; f < f1; f += gridDim.x * MLH_FACE_TILE) {
+        const int i = p.d.fa[f];
+        const int e = p.d.fe[f];
         const int j = e & MLH_NNL_IDX_MASK;
         const int code = PER ? (int)((unsigned)e >> MLH_NNL_IDX_BITS) : 0;
         const int ids = p.d.id[i], idn = p.d.id[j];
@@ -580,21 +671,6 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
             for (int k = 0; k < D; ++k) {
                 xbi[k] = image_coord(xb[k], (cab >> (2 * k)) & 3, p.grid.bmin[k], p.grid.bmax[k]);
                 xai[k] = image_coord(xa[k], (cba >> (2 * k)) & 3, p.grid.bmin[k], p.grid.bmax[k]);
-            }
-            // quirk Q9: is the pair also in the OTHER particle's list?  (the view that is not ours)
-            {
-                bool ex = true;
-                const int cview = reverse_code(code); // image of self as the neighbour sees it
-                const double *xs = canon ? xa : xb, *xn = canon ? xb : xa;
-                double dd[3];
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    const int ck = (cview >> (2 * k)) & 3;
-                    ex = ex && image_exists(xs[k], ck, p.grid.bmin[k], p.grid.bmax[k], p.h);
-                    dd[k] = __dsub_rn(image_coord(xs[k], ck, p.grid.bmin[k], p.grid.bmax[k]), xn[k]);
-                }
-                ex = ex && (dist_sqr_exact<D>(dd) < p.hSqr);
-                if (!ex && !p.symmetric_seam) atomicAdd(&p.d.counters[0], 1u);
             }
         } else {
 #pragma unroll
@@ -726,9 +802,9 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
         }
         if (PER && code != 0 && (Wa[1] < 0. || Wb[1] < 0.)) atomicOr(p.d.flags, MLH_F_NEG_GHOST_PRESSURE);
 
-        // ---- stage the record (slot-major inside the chunk: coalesced here and in K4b/K4c) ----
-        double *rec = stage + (size_t)s * cstride + il;
-        const size_t fs = (size_t)p.max_ni * cstride; // field stride
+        // ---- stage the record (field-major inside the chunk: coalesced here and in K4b) ----
+        double *rec = stage + (f - f0);
+        const size_t fs = (size_t)cstride; // field stride
 #pragma unroll
         for (int nu = 0; nu < NW; ++nu) {
             rec[(R::WA + nu) * fs] = Wa[nu];
@@ -739,7 +815,6 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
             rec[(R::VF + k) * fs] = vF[k];
             rec[(R::AA + k) * fs] = A[k];
         }
-        rec[R::SG * fs] = canon ? 1. : -1.;
     }
 }
 
@@ -771,26 +846,26 @@ __device__ __forceinline__ void face_load(const double *rec, size_t fs, double *
 }
 
 template <int D>
-__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_riemann(const Params p, double *__restrict__ stage, int c0, int cn, int cstride) {
+__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_riemann(const Params p, const double *__restrict__ stage, int f0, int cstride) {
     constexpr int NW = D + 2;
     constexpr int T = MLH_FACE_TILE;
+    constexpr int FREC = MLH_FREC(D);
     using R = FaceRec<D>;
     __shared__ double sh[MLH_RS_FIELDS][T]; // [0..6] problem, [7..13] iteration state of face `slot` (SoA: conflict-free)
     __shared__ int sh_flags[T];             // method | mflag << 2 | vacuum << 3
     __shared__ int sh_list[2][T];           // unfinished faces of the coming round, double buffered
     __shared__ int sh_count[3];             // their number, triple buffered (reset one round ahead)
-    const int tiles_per_slot = (cn + T - 1) / T;
-    const int smax = (int)p.d.counters[3];
-    const int ntiles = tiles_per_slot * smax;
-    const size_t fs = (size_t)p.max_ni * cstride;
+    const int nfaces = min(p.d.face_start[p.own_end], p.fcap);
+    const int f1 = min(nfaces, f0 + cstride);
+    const int ntiles = (f1 - f0 + T - 1) / T;
+    const size_t fs = (size_t)cstride;
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned below = (1u << lane) - 1u;
     bool vacuum = false;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int s = t / tiles_per_slot;
-        const int il = (t - s * tiles_per_slot) * T + tid;
-        const bool valid = il < cn && s < p.d.noi[c0 + (il < cn ? il : 0)] + p.d.noig[c0 + (il < cn ? il : 0)];
-        double *rec = stage + (size_t)s * cstride + il;
+        const int f = f0 + t * T + tid;
+        const bool valid = f < f1;
+        const double *rec = stage + (f - f0);
         int my_method = RS_DONE;
         // ---- stage A: rotate, sound speeds, initial guess, f(0), f(guess): the iteration state goes to shared memory.
         // Nothing else is kept in registers across the rounds (stage C re-reads the L2-hot record), so that 8 blocks
@@ -837,6 +912,13 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_r
             const int nU = sh_count[cur];
             if (nU == 0) break; // uniform across the block
             my_method = RS_DONE;
+            // iterations before the next regrouping: the per-round cost (barrier, compaction, state through shared memory)
+            // is paid by all 128 threads, and the iteration counts are bimodal (Brent: ~3-6, or ~27-29 when it degenerates
+            // to bisection from [0, Pguess]; oracle statistics in DESIGN.md) -- so late rounds run several iterations
+#ifndef MLH_K4B_SCHED
+#define MLH_K4B_SCHED 1
+#endif
+            const int R = !MLH_K4B_SCHED ? 1 : (r < 2 ? 1 : (r < 4 ? 2 : (r < 6 ? 4 : 8)));
             if (tid < nU) {
                 const int f = sh_list[r & 1][tid];
                 my_face = f;
@@ -846,16 +928,20 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_r
                 const int fl = sh_flags[f];
                 it.method = fl & 3;
                 it.mflag = (fl >> 2) & 1;
-                const double trial = rs_iter_trial(it);
-                RsEval e;
                 const double rhoL = sh[0][f], PL = sh[1][f], aL = sh[2][f], rhoR = sh[3][f], PR = sh[4][f], aR = sh[5][f];
-                if (__any_sync(__activemask(), it.method == RS_NEWTON)) {
-                    rs_eval2<true>(p.rs, rhoL, PL, aL, rhoR, PR, aR, trial, e);
-                } else {
-                    rs_eval2<false>(p.rs, rhoL, PL, aL, rhoR, PR, aR, trial, e);
-                    e.fpL = e.fpR = 0.;
+                const double du = sh[6][f];
+                for (int q = 0; q < R; ++q) {
+                    const double trial = rs_iter_trial(it);
+                    RsEval e;
+                    if (__any_sync(__activemask(), it.method == RS_NEWTON)) {
+                        rs_eval2<true>(p.rs, rhoL, PL, aL, rhoR, PR, aR, trial, e);
+                    } else {
+                        rs_eval2<false>(p.rs, rhoL, PL, aL, rhoR, PR, aR, trial, e);
+                        e.fpL = e.fpR = 0.;
+                    }
+                    rs_iter_update(it, trial, e.fL + e.fR + du, e.fpL + e.fpR);
+                    if (it.method == RS_DONE) break;
                 }
-                rs_iter_update(it, trial, e.fL + e.fR + sh[6][f], e.fpL + e.fpR);
                 sh[7][f] = it.a; sh[8][f] = it.b; sh[9][f] = it.c; sh[10][f] = it.d;
                 sh[11][f] = it.fa; sh[12][f] = it.fb; sh[13][f] = it.fc;
                 sh_flags[f] = it.method | (it.mflag << 2);
@@ -867,7 +953,6 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_r
             double Wa[NW], Wb[NW], vF[D], A[D], F[NW];
             FaceFrame<D> fr;
             face_load<D>(rec, fs, Wa, Wb, vF, A);
-            const double sgn = rec[R::SG * fs];
             face_rotate<D>(A, Wa, Wb, fr);
             double rhoSol, uSol, PSol;
             int flag;
@@ -881,8 +966,10 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_r
                 flag = rs_sample(p.rs, q, Wa[2], Wb[2], sh[8][tid], &rhoSol, &uSol, &PSol);
             }
             face_project<D>(p, flag, rhoSol, uSol, PSol, Wa, Wb, fr, vF, A, F);
+            double Fr[FREC];
 #pragma unroll
-            for (int nu = 0; nu < NW; ++nu) rec[(R::FX + nu) * fs] = sgn * F[nu];
+            for (int nu = 0; nu < FREC; ++nu) Fr[nu] = nu < NW ? F[nu] : 0.;
+            store_packed<FREC>(p.d.F + (size_t)f * FREC, Fr);
         }
         __syncthreads(); // sh is rewritten by the next tile
     }
@@ -893,22 +980,27 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_r
 // K4c / K5: collectFluxes (:1926-2008) in list order + updateStateAndPosition (:2013-2110)
 // ---------------------------------------------------------------------------------------------
 template <int D, bool PER>
-__global__ void __launch_bounds__(128) k_flux_sum_update(const Params p, const double *__restrict__ stage, int c0, int cn, int cstride) {
+__global__ void __launch_bounds__(128) k_flux_sum_update(const Params p) {
     constexpr int NW = D + 2;
-    using R = FaceRec<D>;
-    const int il = blockIdx.x * blockDim.x + threadIdx.x;
-    if (il >= cn) return;
-    const int i = c0 + il;
+    constexpr int FREC = MLH_FREC(D);
+    const int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.own_end) return;
     const double dt = *p.d.dt_used;
-    const size_t fs = (size_t)p.max_ni * cstride;
     const int ntot = p.d.noi[i] + p.d.noig[i];
+    const int fs = p.d.face_start[i];
     double acc[NW];
 #pragma unroll
     for (int nu = 0; nu < NW; ++nu) acc[nu] = 0.;
     for (int s = 0; s < ntot; ++s) {
-        const double *rec = stage + (size_t)s * cstride + il;
+        const unsigned v = p.d.fmap[(size_t)s * p.ncap + i];
+        if (v == MLH_FMAP_SKIP) continue;
+        const int f = (v & 2u) ? fs + (int)(v >> 2) : (int)(v >> 2);
+        if (f >= p.fcap) continue; // face capacity exceeded (flag raised by k_face_index)
+        double Fr[FREC];
+        load_packed<FREC>(p.d.F + (size_t)f * FREC, Fr);
+        const double sgn = (v & 1u) ? -1. : 1.;
 #pragma unroll
-        for (int nu = 0; nu < NW; ++nu) acc[nu] += rec[(R::FX + nu) * fs];
+        for (int nu = 0; nu < NW; ++nu) acc[nu] += sgn * Fr[nu];
     }
     if (p.debug_capture) {
         p.d.flux[0][i] = acc[0];
@@ -974,33 +1066,49 @@ int launch_chunks(mlh_ctx *c) {
     const int chunk = c->stage_chunk;
     const int grid_persistent = c->num_sms * 8;
     cudaStream_t st = c->stream;
-    for (int b = 0; b < n; b += chunk) {
-        const int cn = (n - b < chunk) ? n - b : chunk;
-        const int c0 = p.own_begin + b;
+    // The face count lives on the device (face_start[own_end]); without a host round trip the chunk loop covers the
+    // face CAPACITY and the kernels of chunks beyond the last face return at once.  One chunk in the usual case.
+    for (long f0 = 0; f0 < p.fcap; f0 += chunk) {
         mlh_prof_begin(c, KID_FACES);
-        k_face_states<D, PER><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, c0, cn, chunk);
+        k_face_states<D, PER><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, (int)f0, chunk);
         mlh_prof_end(c, KID_FACES);
         mlh_prof_begin(c, KID_FLUX);
-        k_face_riemann<D><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, c0, cn, chunk);
+        k_face_riemann<D><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, (int)f0, chunk);
         mlh_prof_end(c, KID_FLUX);
-        mlh_prof_begin(c, KID_UPDATE);
-        k_flux_sum_update<D, PER><<<mlh_blocks(cn, 128), 128, 0, st>>>(p, c->stage, c0, cn, chunk);
-        mlh_prof_end(c, KID_UPDATE);
     }
+    mlh_prof_begin(c, KID_UPDATE);
+    k_flux_sum_update<D, PER><<<mlh_blocks(n, 128), 128, 0, st>>>(p);
+    mlh_prof_end(c, KID_UPDATE);
     return MLH_OK;
 }
 
 } // namespace
 
-// staging buffer: (5D+7) doubles per (slot, particle) of one chunk
+// face list of this step (after K2): exclusive scan of the owned-slot counts + k_face_index
+int mlh_launch_face_index(mlh_ctx *c) {
+    Params &p = c->p;
+    const int n = p.own_end - p.own_begin;
+    mlh_prof_begin(c, KID_FACE_INDEX);
+    // face_start is indexed by the SRT index; entries below own_begin are never read
+    mlh_exclusive_scan(c, p.d.nown + p.own_begin, p.d.face_start + p.own_begin, p.d.face_scan_tmp, n);
+    if (p.periodic)
+        k_face_index<true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+    else
+        k_face_index<false><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+    mlh_prof_end(c, KID_FACE_INDEX);
+    MLH_CUDA_CHECK(c, cudaGetLastError());
+    return MLH_OK;
+}
+
+// staging buffer: (4D+4) doubles per face of one chunk
 int mlh_stage_alloc(mlh_ctx *c) {
     Params &p = c->p;
-    const size_t per_particle = (size_t)(5 * p.D + 7) * sizeof(double) * (size_t)p.max_ni;
+    const size_t per_face = (size_t)(4 * p.D + 4) * sizeof(double);
     size_t budget = c->cfg.stage_bytes > 0 ? (size_t)c->cfg.stage_bytes : ((size_t)6 << 30);
-    long chunk = (long)(budget / per_particle);
+    long chunk = (long)(budget / per_face);
     chunk = chunk / MLH_FACE_TILE * MLH_FACE_TILE;
     if (chunk < 4 * MLH_FACE_TILE) chunk = 4 * MLH_FACE_TILE;
-    long need = ((long)p.ncap + MLH_FACE_TILE - 1) / MLH_FACE_TILE * MLH_FACE_TILE;
+    long need = ((long)p.fcap + MLH_FACE_TILE - 1) / MLH_FACE_TILE * MLH_FACE_TILE;
     if (chunk > need) chunk = need;
     if (c->stage && chunk == c->stage_chunk) return MLH_OK;
     if (c->stage) {
@@ -1008,10 +1116,10 @@ int mlh_stage_alloc(mlh_ctx *c) {
         cudaFree(c->stage);
         c->stage = nullptr;
     }
-    cudaError_t e = cudaMalloc(&c->stage, per_particle * (size_t)chunk);
+    cudaError_t e = cudaMalloc(&c->stage, per_face * (size_t)chunk);
     if (e != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "cudaMalloc of the %.2f GB face staging buffer failed: %s (lower mlh_config.stage_bytes)",
-                 per_particle * (double)chunk / 1e9, cudaGetErrorString(e));
+                 per_face * (double)chunk / 1e9, cudaGetErrorString(e));
         cudaGetLastError();
         return MLH_E_CUDA;
     }

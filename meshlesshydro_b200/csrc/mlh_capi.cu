@@ -15,7 +15,7 @@ static char g_create_err[512] = "";
 
 static const char *kKernelNames[KID_COUNT] = {
     "k0_bbox",        "k1_cell_key",   "k1_scan",        "k1_scatter_perm", "k1_sort_within_cells",
-    "k1_gather",      "k2_neighbours", "k3_density_matrix", "k3b_gradient_limit", "k4_select_dt",
+    "k1_gather",      "k2_neighbours", "k3_density_matrix", "k3b_gradient_limit", "k2b_face_index", "k4_select_dt",
     "k4a_face_states", "k4b_face_riemann", "k4c_flux_sum_update", "k5_sums", "k5_unpermute", "halo_exchange"};
 static_assert(sizeof(kKernelNames) / sizeof(kKernelNames[0]) == KID_COUNT, "one name per KernelId");
 
@@ -86,6 +86,14 @@ static void carve_pool(mlh_ctx *c, Carver &cv) {
     d.noi = cv.take<int>(n); d.noig = cv.take<int>(n);
     d.ckey = cv.take<int>(n); d.crank = cv.take<int>(n); d.perm = cv.take<int>(n);
     d.nnl = cv.take<int>(n * (size_t)p.max_ni);
+    d.fmap = cv.take<unsigned>(n * (size_t)p.max_ni);
+    d.nnlT = cv.take<int>(n * (size_t)p.max_ni);
+    d.nown = cv.take<int>(n);
+    d.face_start = cv.take<int>(n + 1);
+    d.face_scan_tmp = cv.take<int>(n / 1024 + 4);
+    d.fa = cv.take<int>((size_t)p.fcap);
+    d.fe = cv.take<int>((size_t)p.fcap);
+    d.F = cv.take<double>((size_t)p.fcap * MLH_FREC(D));
     if (p.debug_capture) {
         for (int f = 0; f < 5; ++f) {
             if (f == 3 && D == 2) continue;
@@ -334,6 +342,10 @@ int mlh_create(const mlh_config *cfg, mlh_ctx **out) {
         p.rs.gm1d2 = 0.5 * (g - 1.);
         p.rs.tgdgm1 = 2. * g / (g - 1.);
         p.rs.ginv = 1. / g;
+        p.rs.sqrt_tdgp1 = sqrt(p.rs.tdgp1);
+        p.rs.root_n = 0;
+        for (int n = 5; n <= 7; n += 2)
+            if (fabs(p.rs.gm1d2g * n - 1.) < 4e-16) p.rs.root_n = n;
     }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         snprintf(g_create_err, sizeof(g_create_err), "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -413,6 +425,11 @@ int mlh_upload(mlh_ctx *c, long N, const double *x, const double *y, const doubl
         }
         p.ncap = (int)cap;
         c->capacity = cap;
+        {   // every pair of the lists is one face; pairs inside this rank appear in two lists
+            long long fc = (long long)cap * p.max_ni / 2 + 1024;
+            if (fc > (1LL << 30) - 1) fc = (1LL << 30) - 1;
+            p.fcap = (int)fc;
+        }
         Carver sizing{nullptr, 0};
         carve_pool(c, sizing);
         c->pool_bytes = sizing.off;
@@ -504,6 +521,7 @@ int mlh_neighbours(mlh_ctx *c) {
         return MLH_E_STATE;
     }
     int rc = mlh_launch_neighbours(c);
+    if (rc == MLH_OK) rc = mlh_launch_face_index(c);
     if (rc == MLH_OK) c->phase = 2;
     return rc;
 }

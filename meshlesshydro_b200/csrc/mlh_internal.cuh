@@ -11,6 +11,13 @@
 //            neighbours in the reference's list order, slots [noi, noi+noig) periodic images
 //            ("ghosts") ordered by ascending parent original index (== ascending ghost index of
 //            Particles::ghostNNS).  Entry = sorted index j | image code << 26.
+//   faces:   every pair (i,j) of the lists is ONE face, owned by exactly one of its endpoints (the one
+//            with the lower ORIGINAL index; always self when the partner is a halo particle of
+//            another rank or does not list the pair, quirk Q9).  fmap (slot-major like nnl) maps
+//            each list slot to its face: bits [2..31] value, bit 1 = owned (value = rank among the
+//            owner's owned slots, face index = face_start[i] + rank), else value = global face
+//            index; bit 0 = this endpoint adds -F.  fa/fe = owner index and list entry of face f;
+//            F = fluxes in canonical orientation, AoS MLH_FREC(D) doubles per face.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -22,10 +29,14 @@
 #define MLH_PK2(D) ((D) * (D) + ((D) + 2) * (D))
 #define MLH_NNL_IDX_BITS 26
 #define MLH_NNL_IDX_MASK ((1 << MLH_NNL_IDX_BITS) - 1)
+#define MLH_FREC(D) ((D) == 2 ? 4 : 6)      // doubles per face in the flux array (D+2 used)
+#define MLH_FMAP_SKIP 0xFFFFFFFCu           // slot without a face (partner's list overflowed)
 
 // constants of the restated exact Riemann solver (same expressions as oracle/riemann_exact.h:rs_init)
 struct RsConsts {
     double gamma, gp1d2g, gm1d2g, gm1dgp1, tdgp1, tdgm1, gm1d2, tgdgm1, ginv;
+    double sqrt_tdgp1; // sqrt(2/(gamma+1))
+    int root_n;        // n if (gamma-1)/(2 gamma) == 1/n for n in {5 (gamma=5/3), 7 (gamma=7/5)}, else 0
 };
 
 struct Grid {
@@ -44,6 +55,11 @@ struct DevPtrs {
     double *B[9];   // Binv row-major as used by the reference (Particles.cpp:1249)
     double *g[15];  // gradients: field f in {0 rho,1 vx,2 vy,3 vz,4 P}; component a -> g[f*3+a]
     int *id, *cell, *noi, *noig, *nnl;
+    int *nnlT;      // particle-major copy of nnl (row i at nnlT[i*max_ni ..]): k_face_index searches partners' rows
+    // faces (see header comment)
+    unsigned *fmap;
+    int *nown, *face_start, *face_scan_tmp, *fa, *fe;
+    double *F;
     // packed (AoS) gather records of the SRT set -- what a neighbour visit needs, contiguous per particle so that a
     // gather costs 3 (pk1) + 6 (pk2) 32-byte sectors instead of one sector per scalar array:
     //   pk1[i*PK1 ..] = x[D], v[D], rho, P, cs, omega          (written by K3;  PK1 = 2D+4)
@@ -73,6 +89,7 @@ struct Params {
     int ncur;       // particles in the CUR set
     int ncap;       // capacity (stride of nnl)
     int max_ni;
+    int fcap;       // face capacity (fa, fe, F)
     int slope_limiting, pairwise, mfm, move_particles, abs_mode, q13_mode, q3_mode, symmetric_seam, debug_capture;
     double h, hSqr, gamma, cfl, beta, psi1, psi2;
     double h2, sigma, sigma4; // cubic spline: h/2, normalisation, normalisation/4 (Particles.cpp:10-15)
@@ -191,7 +208,7 @@ __device__ __forceinline__ void neighbour_geometry(const Params &p, const double
 // ---------------------------------------------------------------------------------------------
 enum KernelId {
     KID_BBOX = 0, KID_KEY, KID_SCAN, KID_SCATTER, KID_CELLSORT, KID_GATHER, KID_NEIGHBOURS, KID_DENSITY,
-    KID_GRADIENT, KID_SELECT_DT, KID_FACES, KID_FLUX, KID_UPDATE, KID_SUMS, KID_UNPERMUTE, KID_HALO, KID_COUNT
+    KID_GRADIENT, KID_FACE_INDEX, KID_SELECT_DT, KID_FACES, KID_FLUX, KID_UPDATE, KID_SUMS, KID_UNPERMUTE, KID_HALO, KID_COUNT
 };
 
 struct mlh_ctx {
@@ -204,8 +221,8 @@ struct mlh_ctx {
     int phase;           // 0 = CUR valid (start of step); 1..4 after grid/neighbours/density/gradients
     void *pool;          // single device allocation backing all arrays
     size_t pool_bytes;
-    double *stage;       // face staging buffer of K4 (k4_flux.cu): (5D+7) doubles x max_ni x stage_chunk
-    int stage_chunk;     // particles per K4 chunk (multiple of 128)
+    double *stage;       // face staging buffer of K4 (k4_flux.cu): (4D+4) doubles x stage_chunk
+    int stage_chunk;     // faces per K4 chunk (multiple of 128)
     int num_sms;
     double *dl_scratch;  // un-permutation staging of mlh_download_state (8 x ncap doubles, lazily allocated)
     int max_cells;       // allocated cell-array size
@@ -236,6 +253,9 @@ struct mlh_ctx {
 
 // kernel launchers (each .cu implements its stage)
 int mlh_launch_sort(mlh_ctx *c);        // k1_sort.cu
+// exclusive scan of in[0..n) into out[0..n], out[n] = total; tmp holds n/1024+2 ints (k1_sort.cu)
+int mlh_exclusive_scan(mlh_ctx *c, const int *in, int *out, int *tmp, int n);
+int mlh_launch_face_index(mlh_ctx *c);  // k4_flux.cu (after K2; builds the face list)
 int mlh_launch_neighbours(mlh_ctx *c);  // k2_neighbours.cu
 int mlh_launch_density(mlh_ctx *c);     // k3_density.cu
 int mlh_launch_gradient(mlh_ctx *c);    // k3b_gradient.cu

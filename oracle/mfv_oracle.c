@@ -1267,3 +1267,15 @@ long orc_fetch(void *ctx, const char *name, void *dst) {
 #undef IS
     return -1;
 }
+
+#ifdef RS_STATS
+/* out[0..63] Newton iterations per solve, out[64..127] Brent iterations per Brent call; reset afterwards */
+void orc_rs_stats(long *out) {
+    int k;
+    for (k = 0; k < 64; ++k) {
+        out[k] = rs_stat_newton[k];
+        out[64 + k] = rs_stat_brent[k];
+        rs_stat_newton[k] = rs_stat_brent[k] = 0;
+    }
+}
+#endif

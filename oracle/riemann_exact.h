@@ -133,6 +133,14 @@ static inline double rs_guess_P(const rs_consts *c, double rhoL, double uL, doub
     return Pguess;
 }
 
+#ifdef RS_STATS
+/* optional instrumentation (make RS_STATS=1): histogram of root-finder iterations per solve */
+static long rs_stat_newton[64], rs_stat_brent[64];
+#define RS_STAT_ADD(h, n) ((h)[(n) < 63 ? (n) : 63]++)
+#else
+#define RS_STAT_ADD(h, n) ((void)0)
+#endif
+
 /* Brent's method on [lower, upper] with f(lower)*f(upper) < 0, relative tolerance 5e-9*(a+b) */
 static inline double rs_brent(const rs_consts *cst, double rhoL, double uL, double PL, double aL,
                               double rhoR, double uR, double PR, double aR,
@@ -140,6 +148,7 @@ static inline double rs_brent(const rs_consts *cst, double rhoL, double uL, doub
     double a = lowerlimit, b = upperlimit, c = 0., d = 1e230;
     double fa = lowf, fb = upf, fc = 0., s = 0., fs = 0.;
     int mflag;
+    int nit = 0;
     if (fa * fb > 0.) {
         return b; /* not bracketed: caller's precondition violated, keep upper */
     }
@@ -187,7 +196,10 @@ static inline double rs_brent(const rs_consts *cst, double rhoL, double uL, doub
             double t = a; a = b; b = t;
             t = fa; fa = fb; fb = t;
         }
+        ++nit;
     }
+    RS_STAT_ADD(rs_stat_brent, nit);
+    (void)nit;
     return b;
 }
 
@@ -385,6 +397,7 @@ static inline int rs_solve(const rs_consts *c, double rhoL, double uL, double PL
             ++it;
         }
     }
+    RS_STAT_ADD(rs_stat_newton, it);
     if (1.e6 * fabs(Pstar - Pguess) > 0.5 * (Pstar + Pguess) && fPguess > 0.) {
         Pstar = rs_brent(c, rhoL, uL, PL, aL, rhoR, uR, PR, aR, Pstar, Pguess, fPstar, fPguess);
     } else {

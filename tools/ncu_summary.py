@@ -1,49 +1,31 @@
-"""Summarise an .ncu-rep (read here, no GPU needed) into a small text file for profiles/.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/out.txt"""
-import csv
-import io
-import subprocess
-import sys
-
-KEYS = [
-    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
-    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
-    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed.sum",
-    "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__inst_executed_pipe_fp64.sum",
-    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
-    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
-    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
-    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-    "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__t_bytes.sum",
-    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
-    "smsp__warps_eligible.avg.per_cycle_active", "smsp__average_warp_latency_per_inst_issued.ratio",
-    "sm__cycles_elapsed.max",
-]
-
-
-def main():
-    rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units = rows[0], rows[1]
-    lines = []
-    for r in rows[2:]:
-        d = dict(zip(hdr, r))
-        u = dict(zip(hdr, units))
-        lines.append("kernel: %s  grid %s block %s" % (d.get("Kernel Name"), d.get("Grid Size"), d.get("Block Size")))
-        for k in KEYS:
-            if k in d:
-                lines.append("  %-72s %s %s" % (k, d[k], u.get(k, "")))
-        stalls = sorted(((float(v), k) for k, v in d.items() if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and v),
-                        reverse=True)
-        lines.append("  warp stall reasons (avg warps stalled per issue-active cycle, top 6):")
-        for v, k in stalls[:6]:
-            lines.append("    %-40s %.3f" % (k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
-        lines.append("")
-    open(out, "w").write("\n".join(lines) + "\n")
-    print("\n".join(lines))
-
-
-if __name__ == "__main__":
-    main()
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here on the CPU box): key metrics + top warp-stall reasons.
+usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep [> profiles/x_ncu_full.txt]"""
+import csv, io, subprocess, sys
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fp64.sum",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__data_bank_conflicts_pipe_lsu.sum",
+        "smsp__warps_eligible.avg.per_cycle_active", "smsp__average_warp_latency_per_inst_issued.ratio", "sm__cycles_elapsed.max"]
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units = rows[0], rows[1]
+for r in rows[2:]:
+    d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
+    print("kernel: %s  grid %s block %s" % (d.get("Kernel Name"), d.get("Grid Size"), d.get("Block Size")))
+    for k in KEYS:
+        if k in d: print("  %-72s %s %s" % (k, d[k], u[k]))
+    st = []
+    for k, v in d.items():
+        if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio"):
+            try: st.append((float(v.replace(",", "")), k[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+            except ValueError: pass
+    st.sort(reverse=True)
+    print("  warp stall reasons (avg warps stalled per issue-active cycle, top 6):")
+    for v, k in st[:6]: print("    %-40s %.3f" % (k, v))
