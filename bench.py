@@ -48,6 +48,7 @@ def workloads():
         "sedov128": (lambda: IC.sedov(128), "sedov3d", "Sedov blast 3D MFV, N=128^3"),
         "sedov256": (lambda: IC.sedov(256), "sedov3d", "Sedov blast 3D MFV, N=256^3 (BASELINE configs[4])"),
         "kh100": (lambda: IC.kelvin_helmholtz(100, lattice=False), "kh2d", "Kelvin-Helmholtz 2D MFV, N=10^4 random (BASELINE configs[0] shape)"),
+        "kh1000": (lambda: IC.kelvin_helmholtz(1000, lattice=True, jitter=0.2), "kh2d", "Kelvin-Helmholtz 2D MFV, N=1M jittered lattice"),
         "kh2000": (lambda: IC.kelvin_helmholtz(2000, lattice=True, jitter=0.2), "kh2d", "Kelvin-Helmholtz 2D MFV, N=4M jittered lattice (BASELINE configs[3])"),
         "fb1000": (lambda: IC.fluid_block(1000, jitter=0.05), "fb2d", "fluid-block 2D, N=10^6 (BASELINE configs[2])"),
     }
@@ -181,7 +182,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        side = {"sedov61": 61, "sedov128": 128, "sedov256": 256, "kh100": 100, "kh2000": 2000, "fb1000": 1000}[wname]
+        side = {"sedov61": 61, "sedov128": 128, "sedov256": 256, "kh100": 100, "kh1000": 1000, "kh2000": 2000, "fb1000": 1000}[wname]
         res = time_reference(factory, preset, n_side_weak or side, max(1, args.steps), max(0, min(args.warmup, 1)), budget_s=150.0)
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
@@ -326,7 +327,7 @@ def main():
                "steps": esteps, "ms_per_step": 1e3 * e_s / esteps, "timing": "host wall clock around upload+step+download, pinned buffers"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        side = {"sedov61": 61, "sedov128": 61, "sedov256": 61, "kh100": 100, "kh2000": 200, "fb1000": 200}[wname]
+        side = {"sedov61": 61, "sedov128": 61, "sedov256": 61, "kh100": 100, "kh1000": 200, "kh2000": 200, "fb1000": 200}[wname]
         cpu = time_reference(factory, preset, side, 2, 1, budget_s=25.0)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:

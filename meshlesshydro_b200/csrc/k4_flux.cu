@@ -37,6 +37,7 @@
 // written once and read once).
 #include "mlh_internal.cuh"
 #include <cfloat>
+#include <cuda_pipeline.h>
 
 namespace {
 
@@ -243,6 +244,52 @@ __device__ __forceinline__ void rs_iter_update(RsIter &it, double s, double fs, 
     }
     it.a = a; it.b = b; it.fa = fa; it.fb = fb;
     if (!(!(fb == 0.) && (fabs(a - b) > 5.e-9 * (a + b)))) it.method = RS_DONE;
+}
+
+// f_L(Ps) + f_R(Ps) + du without branches: both sides evaluate the rarefaction AND the shock expression (same
+// formulas as rs_eval2, so the values are identical) and select.  Inside a warp the sides of the 32 faces are a mix of
+// both kinds anyway, so the divergent version executed all four paths with half-empty warps (profiles/r01k); here the
+// two sides are independent instruction streams that overlap in the FP64 pipe.
+__device__ __forceinline__ double rs_f_nobranch(const RsConsts &c, const RsProblem &q, double Ps) {
+    const double wL = rs_root_pow(c, Ps / q.PL), wR = rs_root_pow(c, Ps / q.PR);
+    const double qL = c.sqrt_tdgp1 * rsqrt(q.rhoL * (Ps + c.gm1dgp1 * q.PL));
+    const double qR = c.sqrt_tdgp1 * rsqrt(q.rhoR * (Ps + c.gm1dgp1 * q.PR));
+    const double fL = (Ps > q.PL) ? (Ps - q.PL) * qL : c.tdgm1 * q.aL * (wL - 1.);
+    const double fR = (Ps > q.PR) ? (Ps - q.PR) * qR : c.tdgm1 * q.aR * (wR - 1.);
+    return fL + fR + q.du;
+}
+
+// one Brent iteration (rs_iter_trial + f + rs_iter_update for method == RS_BRENT) with selects instead of branches;
+// same expressions, same decisions
+__device__ __forceinline__ void rs_brent_step(const RsConsts &cst, const RsProblem &q, RsIter &it) {
+    const double a = it.a, b = it.b, c = it.c, d = it.d, fa = it.fa, fb = it.fb, fc = it.fc;
+    const bool mflag = it.mflag != 0;
+    const bool iqi = (fa != fc) & (fb != fc);
+    const double dab = fa - fb, dac = fa - fc, dbc = fb - fc;
+    const double numI = a * fb * fc * dbc - b * fa * fc * dac + c * fa * fb * dab;
+    const double denI = dab * dac * dbc;
+    const double numS = fb * (b - a), denS = fb - fa;
+    const double qv = (iqi ? numI : numS) / (iqi ? denI : denS);
+    double s = iqi ? qv : b - qv;
+    const double tmp2 = 0.25 * (3. * a + b);
+    const bool between = ((s > tmp2) & (s < b)) | ((s < tmp2) & (s > b));
+    const double sb = fabs(s - b), bc = fabs(b - c), cd = fabs(c - d);
+    const bool bis = (!between) | (mflag & (sb >= 0.5 * bc)) | ((!mflag) & (sb >= 0.5 * cd)) | (mflag & (bc < 5.e-9 * (b + c))) |
+                     ((!mflag) & (cd < 5.e-9 * (c + d)));
+    s = bis ? 0.5 * (a + b) : s;
+    it.mflag = bis ? 1 : 0;
+    const double fs = rs_f_nobranch(cst, q, s);
+    it.d = c;
+    it.c = b;
+    it.fc = fb;
+    const bool left = fa * fs < 0.;
+    const double na = left ? a : s, nfa = left ? fa : fs, nb = left ? s : b, nfb = left ? fs : fb;
+    const bool sw = fabs(nfa) < fabs(nfb);
+    it.a = sw ? nb : na;
+    it.fa = sw ? nfb : nfa;
+    it.b = sw ? na : nb;
+    it.fb = sw ? nfa : nfb;
+    if (!(!(it.fb == 0.) && (fabs(it.a - it.b) > 5.e-9 * (it.a + it.b)))) it.method = RS_DONE;
 }
 
 // vacuum sampling (Toro 4.6); cold path
@@ -819,17 +866,26 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4b: one thread per staged record -- the Riemann class of the reference.
-// The number of root-finder iterations per face is strongly non-uniform (Newton 1-3, Brent 3-20 with a long
-// tail) and random inside a warp; run lane-per-face to completion, the warps were 28 % full (ncu,
-// profiles/r01b).  So the iteration state of a 128-face tile lives in shared memory and after EVERY
-// iteration the unfinished faces are re-compacted (ballot + prefix): round r runs ceil(U_r/32) full warps
-// instead of 4 mostly empty ones; Newton faces are listed before Brent faces so warps stay homogeneous.
+// K4b: the Riemann class of the reference, in three kernels so that every warp instruction has (nearly) all of its
+// lanes doing the same thing:
+//   k_face_setup    thread per face: rotate, sound speeds, vacuum test, initial guess, f(0), f(guess).  Faces that need
+//                   no iteration (f(guess) == 0: identical states) get P* at once; the others append their problem
+//                   (7 doubles) and root-finder state (7 doubles + flags) to a queue in HBM.
+//   k_face_iterate  persistent lanes, one queued face per lane, state in registers, NO barriers and no shared
+//                   memory: a lane iterates until its face converges, stores P*, and takes the next queue entry.
+//                   The iteration counts are strongly bimodal (oracle statistics, KH 2D: ~70 % of the faces enter
+//                   Brent, of those half take 3-6 iterations and a third 27-29 because Brent degenerates to bisection
+//                   on [0, Pguess]) -- lane-per-face to completion left warps 28 % full and
+//                   block-level regrouping (previous version, profiles/r01e..r01i) spent half of its warp time at
+//                   barriers.  Here a lane is idle only during the ~50-instruction refill of its neighbours.
+//   k_face_finish   thread per face: star state at x/t = 0, rotation back, projection -> F (canonical orientation).
 // ---------------------------------------------------------------------------------------------
 #define MLH_RS_FIELDS 14
 #ifndef MLH_K4B_BLOCKS_PER_SM
-#define MLH_K4B_BLOCKS_PER_SM 8
+#define MLH_K4B_BLOCKS_PER_SM 6
 #endif
+#define MLH_PSTAR_VACUUM (-1.) // marker in the P* array: vacuum present or generated, solved in k_face_finish
+
 template <int D>
 __device__ __forceinline__ void face_load(const double *rec, size_t fs, double *Wa, double *Wb, double *vF, double *A) {
     using R = FaceRec<D>;
@@ -845,133 +901,227 @@ __device__ __forceinline__ void face_load(const double *rec, size_t fs, double *
     }
 }
 
+// queue layout (chunk-sized, SoA): qd[k * cstride + q], k = 0..6 problem (rhoL, PL, aL, rhoR, PR, aR, du), 7..10 start of
+// the root finder (Pguess, f(Pguess), f(0), f'(Pguess)); qi[q] = face index relative to the chunk.  Faces that start
+// with Newton-Raphson are appended from the front (q = 0, 1, ..), faces that start with Brent from the back
+// (q = cstride-1, cstride-2, ..), so that the warps of k_face_iterate work on one kind at a time.  To keep the
+// append counters from serialising (one L2 atomic per warp and kind), the queue is split into MLH_Q_REGIONS regions
+// of equal capacity with their own pair of counters; the warp-tile of 32 faces number t appends to region t % REGIONS.
+#define MLH_Q_FIELDS 11
+#define MLH_Q_REGIONS 128
+__host__ __device__ __forceinline__ int q_region_cap(int cstride) { // faces per region (multiple of 32)
+    const int nwt = (cstride + 31) / 32;
+    return (nwt + MLH_Q_REGIONS - 1) / MLH_Q_REGIONS * 32;
+}
 template <int D>
-__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_riemann(const Params p, const double *__restrict__ stage, int f0, int cstride) {
+__global__ void __launch_bounds__(MLH_FACE_TILE) k_face_setup(const Params p, const double *__restrict__ stage, double *__restrict__ pstar,
+                                                              double *__restrict__ qd, int *__restrict__ qi, int *__restrict__ qcount,
+                                                              int f0, int cstride) {
     constexpr int NW = D + 2;
-    constexpr int T = MLH_FACE_TILE;
-    constexpr int FREC = MLH_FREC(D);
-    using R = FaceRec<D>;
-    __shared__ double sh[MLH_RS_FIELDS][T]; // [0..6] problem, [7..13] iteration state of face `slot` (SoA: conflict-free)
-    __shared__ int sh_flags[T];             // method | mflag << 2 | vacuum << 3
-    __shared__ int sh_list[2][T];           // unfinished faces of the coming round, double buffered
-    __shared__ int sh_count[3];             // their number, triple buffered (reset one round ahead)
     const int nfaces = min(p.d.face_start[p.own_end], p.fcap);
     const int f1 = min(nfaces, f0 + cstride);
-    const int ntiles = (f1 - f0 + T - 1) / T;
     const size_t fs = (size_t)cstride;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned below = (1u << lane) - 1u;
-    bool vacuum = false;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int f = f0 + t * T + tid;
-        const bool valid = f < f1;
-        const double *rec = stage + (f - f0);
-        int my_method = RS_DONE;
-        // ---- stage A: rotate, sound speeds, initial guess, f(0), f(guess): the iteration state goes to shared memory.
-        // Nothing else is kept in registers across the rounds (stage C re-reads the L2-hot record), so that 8 blocks
-        // fit on an SM and the few warps that are busy in late rounds still hide the FP64 latencies.
+    const int lane = threadIdx.x & 31;
+    const int nround = (f1 - f0 + 31) / 32 * 32; // whole warps stay in the loop (ballots below)
+    const int rcap = q_region_cap(cstride);
+    for (int fl = blockIdx.x * MLH_FACE_TILE + threadIdx.x; fl < nround; fl += gridDim.x * MLH_FACE_TILE) {
+        const bool valid = f0 + fl < f1;
+        int method = RS_DONE;
+        RsProblem q;
+        RsIter it;
         if (valid) {
             double Wa[NW], Wb[NW], vF[D], A[D];
             FaceFrame<D> fr;
-            face_load<D>(rec, fs, Wa, Wb, vF, A);
+            face_load<D>(stage + fl, fs, Wa, Wb, vF, A);
             face_rotate<D>(A, Wa, Wb, fr);
-            RsProblem q;
             // left = canonical particle a, right = b, along +A (Riemann.cpp:93-94)
             if (rs_setup(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], q)) {
-                RsIter it;
                 rs_iter_begin(q, it);
-                my_method = it.method;
-                sh[0][tid] = q.rhoL; sh[1][tid] = q.PL; sh[2][tid] = q.aL;
-                sh[3][tid] = q.rhoR; sh[4][tid] = q.PR; sh[5][tid] = q.aR; sh[6][tid] = q.du;
-                sh[7][tid] = it.a; sh[8][tid] = it.b; sh[9][tid] = it.c; sh[10][tid] = it.d;
-                sh[11][tid] = it.fa; sh[12][tid] = it.fb; sh[13][tid] = it.fc;
-                sh_flags[tid] = it.method | (it.mflag << 2);
+                method = it.method;
+                if (method == RS_DONE) pstar[fl] = it.b;
             } else {
-                sh_flags[tid] = 8; // vacuum generated or present: solved in stage C
+                pstar[fl] = MLH_PSTAR_VACUUM;
             }
         }
-        // ---- stage B: iterate; the list of unfinished faces is rebuilt after every round (one barrier per round) ----
-        int my_face = tid; // the face this thread iterated last
-        if (tid == 0) {
-            sh_count[0] = 0;
-            sh_count[1] = 0;
-        }
-        __syncthreads();
-        for (int r = 0;; ++r) {
-            const int cur = r % 3;
-            const unsigned act = __ballot_sync(0xffffffffu, my_method != RS_DONE);
-            if (act) {
-                int base = 0;
-                if (lane == __ffs(act) - 1) base = atomicAdd(&sh_count[cur], __popc(act));
-                base = __shfl_sync(0xffffffffu, base, __ffs(act) - 1);
-                if (my_method != RS_DONE) sh_list[r & 1][base + __popc(act & below)] = my_face;
-            }
-            __syncthreads();
-            // counter of round r+2 (= of round r-1): every thread read it before arriving at this barrier
-            if (tid == 0) sh_count[(r + 2) % 3] = 0;
-            const int nU = sh_count[cur];
-            if (nU == 0) break; // uniform across the block
-            my_method = RS_DONE;
-            // iterations before the next regrouping: the per-round cost (barrier, compaction, state through shared memory)
-            // is paid by all 128 threads, and the iteration counts are bimodal (Brent: ~3-6, or ~27-29 when it degenerates
-            // to bisection from [0, Pguess]; oracle statistics in DESIGN.md) -- so late rounds run several iterations
-#ifndef MLH_K4B_SCHED
-#define MLH_K4B_SCHED 1
-#endif
-            const int R = !MLH_K4B_SCHED ? 1 : (r < 2 ? 1 : (r < 4 ? 2 : (r < 6 ? 4 : 8)));
-            if (tid < nU) {
-                const int f = sh_list[r & 1][tid];
-                my_face = f;
-                RsIter it;
-                it.a = sh[7][f]; it.b = sh[8][f]; it.c = sh[9][f]; it.d = sh[10][f];
-                it.fa = sh[11][f]; it.fb = sh[12][f]; it.fc = sh[13][f];
-                const int fl = sh_flags[f];
-                it.method = fl & 3;
-                it.mflag = (fl >> 2) & 1;
-                const double rhoL = sh[0][f], PL = sh[1][f], aL = sh[2][f], rhoR = sh[3][f], PR = sh[4][f], aR = sh[5][f];
-                const double du = sh[6][f];
-                for (int q = 0; q < R; ++q) {
-                    const double trial = rs_iter_trial(it);
-                    RsEval e;
-                    if (__any_sync(__activemask(), it.method == RS_NEWTON)) {
-                        rs_eval2<true>(p.rs, rhoL, PL, aL, rhoR, PR, aR, trial, e);
-                    } else {
-                        rs_eval2<false>(p.rs, rhoL, PL, aL, rhoR, PR, aR, trial, e);
-                        e.fpL = e.fpR = 0.;
-                    }
-                    rs_iter_update(it, trial, e.fL + e.fR + du, e.fpL + e.fpR);
-                    if (it.method == RS_DONE) break;
-                }
-                sh[7][f] = it.a; sh[8][f] = it.b; sh[9][f] = it.c; sh[10][f] = it.d;
-                sh[11][f] = it.fa; sh[12][f] = it.fb; sh[13][f] = it.fc;
-                sh_flags[f] = it.method | (it.mflag << 2);
-                my_method = it.method;
-            }
-        }
-        // ---- stage C: star state at x/t = 0, rotation back, projection ----
-        if (valid) {
-            double Wa[NW], Wb[NW], vF[D], A[D], F[NW];
-            FaceFrame<D> fr;
-            face_load<D>(rec, fs, Wa, Wb, vF, A);
-            face_rotate<D>(A, Wa, Wb, fr);
-            double rhoSol, uSol, PSol;
-            int flag;
-            if (sh_flags[tid] & 8) {
-                flag = rs_solve_vacuum(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], &rhoSol, &uSol, &PSol);
-                vacuum = vacuum || flag == 0;
-            } else {
-                RsProblem q;
-                q.rhoL = sh[0][tid]; q.PL = sh[1][tid]; q.aL = sh[2][tid];
-                q.rhoR = sh[3][tid]; q.PR = sh[4][tid]; q.aR = sh[5][tid]; q.du = sh[6][tid];
-                flag = rs_sample(p.rs, q, Wa[2], Wb[2], sh[8][tid], &rhoSol, &uSol, &PSol);
-            }
-            face_project<D>(p, flag, rhoSol, uSol, PSol, Wa, Wb, fr, vF, A, F);
-            double Fr[FREC];
 #pragma unroll
-            for (int nu = 0; nu < FREC; ++nu) Fr[nu] = nu < NW ? F[nu] : 0.;
-            store_packed<FREC>(p.d.F + (size_t)f * FREC, Fr);
+        for (int kind = RS_NEWTON; kind <= RS_BRENT; ++kind) {
+            const bool mine = method == kind;
+            const unsigned m = __ballot_sync(0xffffffffu, mine);
+            if (!m) continue;
+            const int region = (fl >> 5) % MLH_Q_REGIONS;
+            int base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(qcount + 2 * region + (kind - RS_NEWTON), __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (mine) {
+                int at = base + __popc(m & ((1u << lane) - 1u));
+                at = region * rcap + (kind == RS_BRENT ? rcap - 1 - at : at);
+                double *d = qd + at;
+                const size_t qs = (size_t)MLH_Q_REGIONS * rcap; // field stride of the queue
+                d[0 * qs] = q.rhoL; d[1 * qs] = q.PL; d[2 * qs] = q.aL; d[3 * qs] = q.rhoR; d[4 * qs] = q.PR; d[5 * qs] = q.aR;
+                d[6 * qs] = q.du;
+                d[7 * qs] = kind == RS_NEWTON ? it.fa : it.a;
+                d[8 * qs] = it.b;
+                d[9 * qs] = kind == RS_NEWTON ? it.fb : it.fa;
+                d[10 * qs] = kind == RS_NEWTON ? it.c : it.fb;
+                qi[at] = fl;
+            }
         }
-        __syncthreads(); // sh is rewritten by the next tile
+    }
+}
+
+// One queued face per lane, iteration state in registers, no block-level synchronisation.  Each warp owns a ring of
+// 64 queue entries in shared memory that it fills 32 entries at a time with cp.async (one coalesced request per
+// field, in flight while the lanes iterate); a lane whose face has converged stores P* and takes the next ring entry.
+// [A per-lane refill straight from HBM fetched a 128-byte line for every 8-byte field: 37 GB of DRAM reads for a
+// 3.7 GB queue and the whole warp waiting on them every pass -- profiles/r01j.]
+#define MLH_RING 64
+__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_iterate(const Params p, double *__restrict__ pstar, const double *__restrict__ qd,
+                                                                                       const int *__restrict__ qi, const int *__restrict__ qcount, int cstride) {
+    __shared__ double ring_d[MLH_FACE_TILE / 32][MLH_Q_FIELDS][MLH_RING];
+    __shared__ int ring_i[MLH_FACE_TILE / 32][MLH_RING];
+    __shared__ char ring_k[MLH_FACE_TILE / 32][MLH_RING]; // how the entry starts: RS_NEWTON | RS_BRENT
+    // batches of <= 32 entries: first the Newton starts of all regions, then the Brent starts.  pre[k] = number of
+    // batches before (kind, region) pair k = kind * REGIONS + region.
+    __shared__ int pre[2 * MLH_Q_REGIONS + 1];
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < 2 * MLH_Q_REGIONS; ++k) {
+            pre[k] = acc;
+            acc += (qcount[2 * (k % MLH_Q_REGIONS) + k / MLH_Q_REGIONS] + 31) / 32;
+        }
+        pre[2 * MLH_Q_REGIONS] = acc;
+    }
+    __syncthreads();
+    const int NB = pre[2 * MLH_Q_REGIONS];
+    const int rcap = q_region_cap(cstride);
+    const size_t fs = (size_t)MLH_Q_REGIONS * rcap; // field stride of the queue
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned below = (1u << lane) - 1u;
+    const int W = gridDim.x * (MLH_FACE_TILE / 32);
+    int bq = blockIdx.x * (MLH_FACE_TILE / 32) + wib; // this warp's next batch (bq, bq + W, ..)
+    int head = 0, avail = 0, pend = 0;                // ring: first ready slot, ready entries, entries in flight
+    double (*rd)[MLH_RING] = ring_d[wib];
+    int *ri = ring_i[wib];
+    char *rk = ring_k[wib];
+    int face = -1;
+    RsProblem q;
+    q.rhoL = q.PL = q.aL = q.rhoR = q.PR = q.aR = 1.;
+    q.du = q.Pguess = q.fPguess = q.f0 = q.fpsum = 0.;
+    RsIter it;
+    it.method = RS_DONE;
+    it.mflag = 0;
+    it.a = it.b = it.c = it.d = it.fa = it.fb = it.fc = 0.;
+    for (;;) {
+        // ---- prefetch the next batch while at most half of the ring is occupied ----
+        if (pend == 0 && avail <= MLH_RING - 32 && bq < NB) {
+            int k = 0; // largest k with pre[k] <= bq
+#pragma unroll
+            for (int step = MLH_Q_REGIONS; step > 0; step >>= 1)
+                if (k + step <= 2 * MLH_Q_REGIONS - 1 && pre[k + step] <= bq) k += step;
+            const bool newton = k < MLH_Q_REGIONS;
+            const int region = newton ? k : k - MLH_Q_REGIONS;
+            const int e = 32 * (bq - pre[k]) + lane;
+            const int cnt = min(32, qcount[2 * region + (newton ? 0 : 1)] - (e - lane));
+            if (lane < cnt) {
+                const int src = region * rcap + (newton ? e : rcap - 1 - e);
+                const int slot = (head + avail + lane) & (MLH_RING - 1);
+#pragma unroll
+                for (int k = 0; k < MLH_Q_FIELDS; ++k) __pipeline_memcpy_async(&rd[k][slot], qd + k * fs + src, 8);
+                __pipeline_memcpy_async(&ri[slot], qi + src, 4);
+                rk[slot] = newton ? RS_NEWTON : RS_BRENT;
+            }
+            __pipeline_commit();
+            pend = cnt;
+            bq += W;
+        }
+        // ---- lanes whose face has converged store P* and take the next ring entry ----
+        const bool done = it.method == RS_DONE;
+        if (done && face >= 0) {
+            pstar[face] = it.b;
+            face = -1;
+        }
+        const unsigned need = __ballot_sync(0xffffffffu, done);
+        if (need) {
+            const int n = __popc(need);
+            if (avail < n && pend) {
+                __pipeline_wait_prior(0);
+                __syncwarp();
+                avail += pend;
+                pend = 0;
+            }
+            const int rank = __popc(need & below);
+            if (done && rank < avail) {
+                const int slot = (head + rank) & (MLH_RING - 1);
+                q.rhoL = rd[0][slot]; q.PL = rd[1][slot]; q.aL = rd[2][slot]; q.rhoR = rd[3][slot]; q.PR = rd[4][slot];
+                q.aR = rd[5][slot]; q.du = rd[6][slot];
+                const double v0 = rd[7][slot], v1 = rd[8][slot], v2 = rd[9][slot], v3 = rd[10][slot];
+                face = ri[slot];
+                const bool nw = rk[slot] == RS_NEWTON;
+                it.method = nw ? RS_NEWTON : RS_BRENT;
+                it.mflag = nw ? 0 : 1;
+                it.a = nw ? 0. : v0;  // Newton: Pstar = 0, f(0); Pguess, f(Pguess), f'(Pguess)
+                it.fa = nw ? v0 : v2; // Brent: a, b, fa, fb as rs_brent_begin left them, c = a, fc = fa
+                it.b = v1;
+                it.fb = nw ? v2 : v3;
+                it.c = nw ? v3 : v0;
+                it.fc = nw ? 0. : v2;
+                it.d = nw ? 0. : 1e230;
+            }
+            const int taken = min(n, avail);
+            head = (head + taken) & (MLH_RING - 1);
+            avail -= taken;
+            __syncwarp(); // the slots just read may be overwritten by the next prefetch
+        }
+        const bool active = it.method != RS_DONE;
+        if (!__any_sync(0xffffffffu, active)) {
+            if (pend == 0 && avail == 0 && bq >= NB) break;
+            continue;
+        }
+        if (active) {
+            if (__any_sync(__activemask(), it.method == RS_NEWTON)) { // Newton starts come first, batch-wise
+                const double trial = rs_iter_trial(it);
+                RsEval e;
+                rs_eval2<true>(p.rs, q.rhoL, q.PL, q.aL, q.rhoR, q.PR, q.aR, trial, e);
+                rs_iter_update(it, trial, e.fL + e.fR + q.du, e.fpL + e.fpR);
+            } else {
+                rs_brent_step(p.rs, q, it);
+            }
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(MLH_FACE_TILE) k_face_finish(const Params p, const double *__restrict__ stage, const double *__restrict__ pstar,
+                                                               int f0, int cstride) {
+    constexpr int NW = D + 2;
+    constexpr int FREC = MLH_FREC(D);
+    const int nfaces = min(p.d.face_start[p.own_end], p.fcap);
+    const int f1 = min(nfaces, f0 + cstride);
+    const size_t fs = (size_t)cstride;
+    bool vacuum = false;
+    for (int f = f0 + blockIdx.x * MLH_FACE_TILE + threadIdx.x; f < f1; f += gridDim.x * MLH_FACE_TILE) {
+        double Wa[NW], Wb[NW], vF[D], A[D], F[NW];
+        FaceFrame<D> fr;
+        face_load<D>(stage + (f - f0), fs, Wa, Wb, vF, A);
+        face_rotate<D>(A, Wa, Wb, fr);
+        const double Ps = pstar[f - f0];
+        double rhoSol, uSol, PSol;
+        int flag;
+        if (Ps == MLH_PSTAR_VACUUM) {
+            flag = rs_solve_vacuum(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], &rhoSol, &uSol, &PSol);
+            vacuum = vacuum || flag == 0;
+        } else {
+            RsProblem q;
+            q.rhoL = Wa[0]; q.PL = Wa[1]; q.rhoR = Wb[0]; q.PR = Wb[1];
+            q.aL = sqrt(p.rs.gamma * q.PL / q.rhoL); // as rs_setup
+            q.aR = sqrt(p.rs.gamma * q.PR / q.rhoR);
+            flag = rs_sample(p.rs, q, Wa[2], Wb[2], Ps, &rhoSol, &uSol, &PSol);
+        }
+        face_project<D>(p, flag, rhoSol, uSol, PSol, Wa, Wb, fr, vF, A, F);
+        double Fr[FREC];
+#pragma unroll
+        for (int nu = 0; nu < FREC; ++nu) Fr[nu] = nu < NW ? F[nu] : 0.;
+        store_packed<FREC>(p.d.F + (size_t)f * FREC, Fr);
     }
     if (vacuum) atomicOr(p.d.flags, MLH_F_VACUUM);
 }
@@ -1072,9 +1222,21 @@ int launch_chunks(mlh_ctx *c) {
         mlh_prof_begin(c, KID_FACES);
         k_face_states<D, PER><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, (int)f0, chunk);
         mlh_prof_end(c, KID_FACES);
+        double *pstar = c->stage + (size_t)FaceRec<D>::NREC * chunk;
+        double *qd = pstar + chunk;
+        const size_t qs = (size_t)MLH_Q_REGIONS * q_region_cap(chunk);
+        int *qi = (int *)(qd + (size_t)MLH_Q_FIELDS * qs);
+        int *qcount = qi + qs;
+        cudaMemsetAsync(qcount, 0, 2 * MLH_Q_REGIONS * sizeof(int), st);
+        mlh_prof_begin(c, KID_FLUX_SETUP);
+        k_face_setup<D><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, pstar, qd, qi, qcount, (int)f0, chunk);
+        mlh_prof_end(c, KID_FLUX_SETUP);
         mlh_prof_begin(c, KID_FLUX);
-        k_face_riemann<D><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, (int)f0, chunk);
+        k_face_iterate<<<c->num_sms * MLH_K4B_BLOCKS_PER_SM, MLH_FACE_TILE, 0, st>>>(p, pstar, qd, qi, qcount, chunk);
         mlh_prof_end(c, KID_FLUX);
+        mlh_prof_begin(c, KID_FLUX_FINISH);
+        k_face_finish<D><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, pstar, (int)f0, chunk);
+        mlh_prof_end(c, KID_FLUX_FINISH);
     }
     mlh_prof_begin(c, KID_UPDATE);
     k_flux_sum_update<D, PER><<<mlh_blocks(n, 128), 128, 0, st>>>(p);
@@ -1100,23 +1262,25 @@ int mlh_launch_face_index(mlh_ctx *c) {
     return MLH_OK;
 }
 
-// staging buffer: (4D+4) doubles per face of one chunk
+// staging buffer per face of one chunk: record (4D+4 doubles), P*, solver queue (11 doubles + 1 int)
 int mlh_stage_alloc(mlh_ctx *c) {
     Params &p = c->p;
-    const size_t per_face = (size_t)(4 * p.D + 4) * sizeof(double);
+    const size_t per_face = (size_t)(4 * p.D + 4 + 1 + MLH_Q_FIELDS) * sizeof(double) + sizeof(int);
     size_t budget = c->cfg.stage_bytes > 0 ? (size_t)c->cfg.stage_bytes : ((size_t)6 << 30);
     long chunk = (long)(budget / per_face);
     chunk = chunk / MLH_FACE_TILE * MLH_FACE_TILE;
     if (chunk < 4 * MLH_FACE_TILE) chunk = 4 * MLH_FACE_TILE;
     long need = ((long)p.fcap + MLH_FACE_TILE - 1) / MLH_FACE_TILE * MLH_FACE_TILE;
     if (chunk > need) chunk = need;
+    if (chunk > (1L << 28) - MLH_FACE_TILE) chunk = (1L << 28) - MLH_FACE_TILE; // queue entries pack the face index into 28 bits
     if (c->stage && chunk == c->stage_chunk) return MLH_OK;
     if (c->stage) {
         cudaStreamSynchronize(c->stream);
         cudaFree(c->stage);
         c->stage = nullptr;
     }
-    cudaError_t e = cudaMalloc(&c->stage, per_face * (size_t)chunk);
+    // the queue regions round the chunk up to a multiple of 32 * MLH_Q_REGIONS faces
+    cudaError_t e = cudaMalloc(&c->stage, per_face * ((size_t)chunk + 32 * MLH_Q_REGIONS) + 2 * MLH_Q_REGIONS * sizeof(int) + 256);
     if (e != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "cudaMalloc of the %.2f GB face staging buffer failed: %s (lower mlh_config.stage_bytes)",
                  per_face * (double)chunk / 1e9, cudaGetErrorString(e));

@@ -16,7 +16,7 @@ static char g_create_err[512] = "";
 static const char *kKernelNames[KID_COUNT] = {
     "k0_bbox",        "k1_cell_key",   "k1_scan",        "k1_scatter_perm", "k1_sort_within_cells",
     "k1_gather",      "k2_neighbours", "k3_density_matrix", "k3b_gradient_limit", "k2b_face_index", "k4_select_dt",
-    "k4a_face_states", "k4b_face_riemann", "k4c_flux_sum_update", "k5_sums", "k5_unpermute", "halo_exchange"};
+    "k4a_face_states", "k4b1_face_setup", "k4b_face_riemann", "k4b3_face_finish", "k4c_flux_sum_update", "k5_sums", "k5_unpermute", "halo_exchange"};
 static_assert(sizeof(kKernelNames) / sizeof(kKernelNames[0]) == KID_COUNT, "one name per KernelId");
 
 // ------------------------------------------------------------------------------------------------

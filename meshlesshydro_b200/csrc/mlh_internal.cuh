@@ -208,7 +208,7 @@ __device__ __forceinline__ void neighbour_geometry(const Params &p, const double
 // ---------------------------------------------------------------------------------------------
 enum KernelId {
     KID_BBOX = 0, KID_KEY, KID_SCAN, KID_SCATTER, KID_CELLSORT, KID_GATHER, KID_NEIGHBOURS, KID_DENSITY,
-    KID_GRADIENT, KID_FACE_INDEX, KID_SELECT_DT, KID_FACES, KID_FLUX, KID_UPDATE, KID_SUMS, KID_UNPERMUTE, KID_HALO, KID_COUNT
+    KID_GRADIENT, KID_FACE_INDEX, KID_SELECT_DT, KID_FACES, KID_FLUX_SETUP, KID_FLUX, KID_FLUX_FINISH, KID_UPDATE, KID_SUMS, KID_UNPERMUTE, KID_HALO, KID_COUNT
 };
 
 struct mlh_ctx {
@@ -221,7 +221,7 @@ struct mlh_ctx {
     int phase;           // 0 = CUR valid (start of step); 1..4 after grid/neighbours/density/gradients
     void *pool;          // single device allocation backing all arrays
     size_t pool_bytes;
-    double *stage;       // face staging buffer of K4 (k4_flux.cu): (4D+4) doubles x stage_chunk
+    double *stage;       // face staging buffer of K4 (k4_flux.cu): record, P*, solver queue x stage_chunk
     int stage_chunk;     // faces per K4 chunk (multiple of 128)
     int num_sms;
     double *dl_scratch;  // un-permutation staging of mlh_download_state (8 x ncap doubles, lazily allocated)
