@@ -128,10 +128,21 @@ int mlh_flux_update(mlh_ctx *ctx, double dt);
 int mlh_prepare(mlh_ctx *ctx, double *dt_cfl);
 /* phases 9-16 with the given dt */
 int mlh_advance(mlh_ctx *ctx, double dt);
-/* prepare + dt policy + advance without a host round trip for dt: dt_fixed>0 -> that value
- * (ADAPTIVE_TIMESTEP 0); else the CFL dt, clipped to dt_max if dt_max>0 (dump-time clipping,
+/* prepare + dt policy + advance without a host round trip for dt: dt_fixed>=0 -> that value
+ * (ADAPTIVE_TIMESTEP 0); negative: the CFL dt, clipped to dt_max if dt_max>0 (dump-time clipping,
  * MeshlessScheme.cpp:94-101).  dt_used may be NULL (no synchronisation then). */
 int mlh_step(mlh_ctx *ctx, double dt_fixed, double dt_max, double *dt_used);
+
+/*
+ * Stand-alone face solver = the reference's Riemann class for a batch of n faces (Riemann.h:19-26):
+ * for each face `Riemann{WR, WL, vFrame, Aij, i}.exact(Fij, gamma)` with gamma / MESHLESS_FINITE_MASS of the context
+ * (Riemann.cpp:7-229 incl. the exact solver behind RiemannSolver::solve, Riemann.cpp:93-94).  Same argument roles as
+ * the class: WL = left state of the solver (the caller's WijR, quirk Q5), WR = right state; W = [rho, P, vx, vy(, vz)]
+ * per face (n x (DIM+2)), vFrame and Aij n x DIM, Fij n x (DIM+2) = [mass, energy, px, py(, pz)].  The inputs are not
+ * modified (the class rotates WR/WL in place; the host mirror does that itself).  Works on a context without particles.
+ */
+int mlh_riemann_faces(mlh_ctx *ctx, long n, const double *WR, const double *WL, const double *vFrame, const double *Aij,
+                      double *Fij);
 
 /* ---- results ---- */
 /* current state in ORIGINAL particle order (of this rank's uploaded/owned ids; ids_out optional) */

@@ -84,6 +84,7 @@ def load_library():
         "mlh_host_alloc": (C.c_int, [C.c_ulong, C.POINTER(vp)]),
         "mlh_host_free": (C.c_int, [vp]),
         "mlh_measure_fp64_peak": (C.c_int, [C.c_int, c_dp]),
+        "mlh_riemann_faces": (C.c_int, [vp, C.c_long] + [c_dp] * 5),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -99,7 +100,7 @@ EXPORTED_SYMBOLS = [
     "mlh_flux_update", "mlh_prepare", "mlh_advance", "mlh_step", "mlh_download_state", "mlh_download_diag", "mlh_sums",
     "mlh_num_particles", "mlh_grid_info", "mlh_debug_fetch", "mlh_stream", "mlh_synchronize", "mlh_profile_enable",
     "mlh_profile_read", "mlh_launch_count", "mlh_timer_start", "mlh_timer_stop", "mlh_comm_unique_id", "mlh_comm_init",
-    "mlh_slab_range", "mlh_host_alloc", "mlh_host_free", "mlh_measure_fp64_peak",
+    "mlh_slab_range", "mlh_host_alloc", "mlh_host_free", "mlh_measure_fp64_peak", "mlh_riemann_faces",
 ]
 
 _INT_FIELDS = {"cell", "noi", "noiGhosts", "sorted_index", "nnl", "nnlGhosts", "nnlGhostCodes"}
@@ -285,6 +286,17 @@ class MfvGpu:
         return out
 
     # ---- measurement ----
+    def riemann_faces(self, WR, WL, vFrame, Aij):
+        """Riemann{WR, WL, vFrame, Aij}.exact for n faces (mlh_riemann_faces); arrays n x (D+2) / n x D."""
+        WR = np.ascontiguousarray(WR, dtype=np.float64)
+        WL = np.ascontiguousarray(WL, dtype=np.float64)
+        vF = np.ascontiguousarray(vFrame, dtype=np.float64)
+        A = np.ascontiguousarray(Aij, dtype=np.float64)
+        n = WR.shape[0]
+        F = np.empty_like(WR)
+        self._check(self.lib.mlh_riemann_faces(self.ctx, n, _dp(WR), _dp(WL), _dp(vF), _dp(A), _dp(F)), "mlh_riemann_faces")
+        return F
+
     def synchronize(self):
         self._check(self.lib.mlh_synchronize(self.ctx), "mlh_synchronize")
 

@@ -585,7 +585,7 @@ __device__ __forceinline__ void face_project(const Params &p, int flag, double r
 // device-side dt policy (MeshlessScheme.cpp:91-105): fixed dt, or CFL dt clipped to dt_max
 __global__ void k_select_dt(const Params p, double dt_fixed, double dt_max) {
     double dt;
-    if (dt_fixed > 0.) {
+    if (dt_fixed >= 0.) { // 0 is a legal step: the reference driver takes a zero-length step at every dump time (quirk Q7)
         dt = dt_fixed;
     } else {
         dt = __longlong_as_double((long long)*p.d.dt_bits);
@@ -1310,4 +1310,101 @@ int mlh_launch_flux(mlh_ctx *c, double dt_fixed, double dt_max) {
     MLH_CUDA_CHECK(c, cudaGetLastError());
     p.ncur = n;
     return MLH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone face solver (mlh_riemann_faces): the Riemann class of the reference for a batch of faces
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <int D>
+__global__ void k_pack_faces(const double *__restrict__ WL, const double *__restrict__ WR, const double *__restrict__ vF,
+                             const double *__restrict__ A, double *__restrict__ stage, int n, int cstride) {
+    using R = FaceRec<D>;
+    constexpr int NW = D + 2;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const size_t fs = (size_t)cstride;
+    for (int nu = 0; nu < NW; ++nu) {
+        stage[(R::WA + nu) * fs + f] = WL[(size_t)f * NW + nu];
+        stage[(R::WB + nu) * fs + f] = WR[(size_t)f * NW + nu];
+    }
+    for (int k = 0; k < D; ++k) {
+        stage[(R::VF + k) * fs + f] = vF[(size_t)f * D + k];
+        stage[(R::AA + k) * fs + f] = A[(size_t)f * D + k];
+    }
+}
+template <int D>
+__global__ void k_unpack_fluxes(const double *__restrict__ F, double *__restrict__ out, int n) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    for (int nu = 0; nu < D + 2; ++nu) out[(size_t)f * (D + 2) + nu] = F[(size_t)f * MLH_FREC(D) + nu];
+}
+
+template <int D>
+int riemann_faces(mlh_ctx *c, int n, const double *hWL, const double *hWR, const double *hvF, const double *hA, double *hF) {
+    constexpr int NW = D + 2;
+    cudaStream_t st = c->stream;
+    const int chunk = (n + MLH_FACE_TILE - 1) / MLH_FACE_TILE * MLH_FACE_TILE;
+    const size_t qs = (size_t)MLH_Q_REGIONS * q_region_cap(chunk);
+    const size_t nd_in = (size_t)n * (2 * NW + 2 * D);
+    const size_t doubles = nd_in + (size_t)FaceRec<D>::NREC * chunk + chunk + MLH_Q_FIELDS * qs + (size_t)n * MLH_FREC(D) + (size_t)n * NW;
+    const size_t bytes = doubles * sizeof(double) + (qs + 2 * MLH_Q_REGIONS + 8) * sizeof(int);
+    char *buf = nullptr;
+    MLH_CUDA_CHECK(c, cudaMalloc(&buf, bytes));
+    double *dWL = (double *)buf, *dWR = dWL + (size_t)n * NW, *dvF = dWR + (size_t)n * NW, *dA = dvF + (size_t)n * D;
+    double *stage = dA + (size_t)n * D;
+    double *pstar = stage + (size_t)FaceRec<D>::NREC * chunk;
+    double *qd = pstar + chunk;
+    double *F = qd + MLH_Q_FIELDS * qs;
+    double *out = F + (size_t)n * MLH_FREC(D);
+    int *qi = (int *)(out + (size_t)n * NW);
+    int *qcount = qi + qs;
+    int *nfaces = qcount + 2 * MLH_Q_REGIONS;
+    cudaMemcpyAsync(dWL, hWL, sizeof(double) * n * NW, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dWR, hWR, sizeof(double) * n * NW, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dvF, hvF, sizeof(double) * n * D, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dA, hA, sizeof(double) * n * D, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(qcount, 0, 2 * MLH_Q_REGIONS * sizeof(int), st);
+    cudaMemcpyAsync(nfaces, &n, sizeof(int), cudaMemcpyHostToDevice, st);
+    // a parameter block whose face list is "n faces, flux array F"
+    Params p = c->p;
+    p.own_end = 0;
+    p.d.face_start = nfaces;
+    p.fcap = n;
+    p.d.F = F;
+    unsigned *flags = nullptr;
+    if (!p.d.flags) { // context without particles: private flag word
+        cudaMalloc(&flags, sizeof(unsigned));
+        cudaMemsetAsync(flags, 0, sizeof(unsigned), st);
+        p.d.flags = flags;
+    }
+    const int grid = mlh_blocks(n, MLH_FACE_TILE);
+    k_pack_faces<D><<<grid, MLH_FACE_TILE, 0, st>>>(dWL, dWR, dvF, dA, stage, n, chunk);
+    k_face_setup<D><<<grid, MLH_FACE_TILE, 0, st>>>(p, stage, pstar, qd, qi, qcount, 0, chunk);
+    k_face_iterate<<<c->num_sms * MLH_K4B_BLOCKS_PER_SM, MLH_FACE_TILE, 0, st>>>(p, pstar, qd, qi, qcount, chunk);
+    k_face_finish<D><<<grid, MLH_FACE_TILE, 0, st>>>(p, stage, pstar, 0, chunk);
+    k_unpack_fluxes<D><<<grid, MLH_FACE_TILE, 0, st>>>(F, out, n);
+    c->launches += 5;
+    cudaMemcpyAsync(hF, out, sizeof(double) * n * NW, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(buf);
+    if (flags) cudaFree(flags);
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+        snprintf(c->err, sizeof(c->err), "mlh_riemann_faces: %s", cudaGetErrorString(e));
+        return MLH_E_CUDA;
+    }
+    return MLH_OK;
+}
+} // namespace
+
+extern "C" int mlh_riemann_faces(mlh_ctx *c, long n, const double *WR, const double *WL, const double *vFrame, const double *Aij,
+                                 double *Fij) {
+    if (!c || n < 0 || (n > 0 && (!WR || !WL || !vFrame || !Aij || !Fij))) return MLH_E_INVALID;
+    if (n == 0) return MLH_OK;
+    if (n > (1L << 27)) {
+        snprintf(c->err, sizeof(c->err), "mlh_riemann_faces: at most 2^27 faces per call");
+        return MLH_E_INVALID;
+    }
+    cudaSetDevice(c->cfg.device);
+    return c->p.D == 2 ? riemann_faces<2>(c, (int)n, WL, WR, vFrame, Aij, Fij) : riemann_faces<3>(c, (int)n, WL, WR, vFrame, Aij, Fij);
 }

@@ -577,8 +577,8 @@ int mlh_flux_update(mlh_ctx *c, double dt) {
         snprintf(c->err, sizeof(c->err), "mlh_flux_update: call mlh_gradients_limit first (phase %d)", c->phase);
         return MLH_E_STATE;
     }
-    if (!(dt > 0.)) {
-        snprintf(c->err, sizeof(c->err), "mlh_flux_update: dt must be > 0");
+    if (!(dt >= 0.)) {
+        snprintf(c->err, sizeof(c->err), "mlh_flux_update: dt must be >= 0");
         return MLH_E_INVALID;
     }
     int rc = mlh_launch_flux(c, dt, -1.);

@@ -1109,7 +1109,7 @@ double orc_step(void *ctx, double dtFixed, double dtMax, int stopAfter) {
     LAP(1);
     density_pressure(o); /* :73-79 */
     LAP(2);
-    if (dtFixed > 0.) {
+    if (dtFixed >= 0.) { /* a zero-length step is what the reference driver does at every dump time (quirk Q7) */
         timeStep = dtFixed;
     } else {
         timeStep = global_timestep(o); /* :93 */

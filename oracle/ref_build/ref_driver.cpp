@@ -129,7 +129,7 @@ void ref_set_capture(void *ctx, int on) { ((RefCtx *)ctx)->capture = on; }
 /*
  * One pass of the loop body of MeshlessScheme::run() (MeshlessScheme.cpp:39-253), minus
  * logging, the snapshot dump (:165-195) and the dump-time clipping of dt (:94-101), which
- * are driver policy.  dtFixed > 0 -> use it (ADAPTIVE_TIMESTEP 0 semantics, :104); else
+ * are driver policy.  dtFixed >= 0 -> use it (ADAPTIVE_TIMESTEP 0 semantics, :104); else
  * dt = compGlobalTimestep (:93), optionally clipped to dtMax if dtMax > 0.
  * stopAfter: 0 = full step; 1 = stop before solveRiemannProblems (state as at the dump point).
  * Returns dt used.
@@ -171,7 +171,7 @@ double ref_step(void *ctx, double dtFixed, double dtMax, int stopAfter) {
     particles->compPressure(c->gamma); // :79
     lap(2);
     double timeStep;
-    if (dtFixed > 0.) {
+    if (dtFixed >= 0.) { /* a zero-length step is what the reference driver does at every dump time (quirk Q7) */
         timeStep = dtFixed;
     } else {
         timeStep = particles->compGlobalTimestep(c->gamma, c->h); // :93
