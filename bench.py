@@ -12,7 +12,7 @@ grows to n_side = round(61 * N^(1/3)) so every GPU keeps ~61^3 particles.
 
 One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events on the library's
 stream), `e2e` = the same metric through the C ABI with HOST (pinned) buffers: upload + step + download
-every step.  `roofline` describes the dominant kernel (k4b_face_riemann, FP64-pipe bound),
+every step.  `roofline` describes the dominant kernel of the per-kernel profile,
 `cpu_baseline` the reference's own sources (oracle/_ref) timed on one host core on a bounded sample.
 `--impl reference` times only that CPU reference arm.
 """
@@ -32,13 +32,8 @@ sys.path.insert(0, ROOT)
 METRIC = "particle_updates_per_s"
 UNIT = "particle-updates/s"
 
-# ---- algorithmic work figures (DESIGN.md section 5) ----
-# doubles read+written per particle-update by the dominant kernel K4+K5
-K4_ALGO_DOUBLES = {2: 24, 3: 38}
-ALL_ALGO_BYTES = {2: 508, 3: 788}
-# FP64 flops the flux kernel needs per face evaluation (DFMA = 2, DADD/DMUL = 1; counted by ncu on the
-# shipped kernel: sm__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on, profiles/r01_*)
-K4_FLOP_PER_FACE = {2: None, 3: None}  # filled from profiles/fp64_per_face.json when present
+# ---- algorithmic work figures (DESIGN.md section 3; SURVEY.md 8d table) ----
+ALL_ALGO_BYTES = {2: 508, 3: 788}  # bytes per particle-update, whole step
 
 
 def workloads():
@@ -195,6 +190,9 @@ def main():
         return 0
 
     # ---------------- B200 arm ----------------
+    # exactly ONE line may reach stdout; libraries (NCCL prints its version banner there) are sent to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from meshlesshydro_b200 import capi
@@ -259,9 +257,10 @@ def main():
         gpu.step(want_dt=False)
     prof = gpu.profile_read()
     gpu.profile(False)
-    noi_mean = float((gpu.fetch("noi").mean() + gpu.fetch("noiGhosts").mean())) if world == 1 else None
-    top = max(prof.items(), key=lambda kv: kv[1][0])
-    k4_ms = prof["k4b_face_riemann"][0] / max(1, prof["k4b_face_riemann"][1])
+    noi_mean = float((gpu.fetch("noi").mean() + gpu.fetch("noiGhosts").mean()))  # rank 0's particles when sharded
+    nfaces = int(gpu.fetch("num_faces")[0])
+    # per STEP (a kernel of the face-chunk loop may launch more than once per step; launches beyond the last face are empty)
+    per_launch = {k: v[0] / psteps for k, v in prof.items() if v[1]}
     step_ms_prof = sum(v[0] for v in prof.values()) / psteps
     peaks = {}
     try:
@@ -269,31 +268,53 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    hbm_src = "of measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "of fallback (B200_PROFILING.md 6.65 TB/s)"
     fp64_peak = capi.fp64_peak_tflops(local_rank)
-    fpf = None
+    ops = {}
     try:
-        fpf = json.load(open(os.path.join(ROOT, "profiles", "fp64_per_face.json")))["flop_per_face"][str(D)]
+        ops = json.load(open(os.path.join(ROOT, "profiles", "fp64_ops.json"))).get(wname, {})
     except Exception:
         pass
-    faces_per_launch = n_local * noi_mean if noi_mean else None
-    roofline = {"kernel": "k4b_face_riemann", "bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
-                "peak_source": "DFMA microbenchmark measured live (mlh_measure_fp64_peak)",
-                "achieved": None, "frac": None, "traffic": None,
-                "share_of_step": k4_ms / step_ms_prof if step_ms_prof else None, "ms_per_launch": k4_ms,
-                "faces_per_launch": faces_per_launch, "flop_per_face": fpf}
-    if fpf and faces_per_launch:
-        roofline["achieved"] = fpf * faces_per_launch / (k4_ms * 1e-3) / 1e12
-        roofline["frac"] = roofline["achieved"] / fp64_peak
-    try:
-        roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "fp64_per_face.json")))["dram_bytes_per_launch"].get(wname)
-    except Exception:
-        pass
-    # HBM view of the same kernel and of the whole step (algorithmic bytes)
+    # ---- roofline of the dominant kernel ----
+    top = max(per_launch.items(), key=lambda kv: prof[kv[0]][0])[0]
+    top_ms = per_launch[top]
+    nslots = n_local * noi_mean if noi_mean else None
+    frec = 4 if D == 2 else 6
+    hbm_models = {  # algorithmic bytes per launch
+        "k4a_face_states": lambda: n_local * (2 * D + 4 + D * D + (D + 2) * D) * 8 + nfaces * ((4 * D + 4) * 8 + 8),
+        "k4c_flux_sum_update": lambda: nslots * (4 + frec * 8) + n_local * 2 * (2 * D + 2) * 8,
+        "k2b_face_index": lambda: nslots * 12 + nfaces * 8,
+        "k1_gather": lambda: n_local * 2 * ((2 * D + 2) * 8 + 8),
+    }
+    roofline = {"kernel": top, "share_of_step": prof[top][0] / psteps / step_ms_prof if step_ms_prof else None,
+                "ms_per_step": top_ms, "launches_per_step": prof[top][1] / psteps, "traffic": None}
+    kops = ops.get(top)
+    if kops:
+        roofline["traffic"] = kops.get("dram_bytes")
+    if top in hbm_models and (nfaces is not None):
+        ab = float(hbm_models[top]())
+        roofline.update({"bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "peak_source": hbm_src,
+                         "algorithmic_bytes_per_step": ab, "achieved": ab / (top_ms * 1e-3) / 1e9})
+        roofline["frac"] = roofline["achieved"] / hbm_peak
+    else:
+        # FP64-pipe bound kernels (north_star: "FP64-pipe utilisation against peak for the Riemann/flux kernel"):
+        # flops = FP64 operations of one launch of this kernel on this workload counted by ncu (DFMA = 2)
+        fl = (2.0 * kops["dfma"] + kops["dmul"] + kops["dadd"]) if kops else None
+        roofline.update({"bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
+                         "peak_source": "of measured (DFMA microbenchmark run live, mlh_measure_fp64_peak)",
+                         "flop_per_step": fl, "achieved": fl / (top_ms * 1e-3) / 1e12 if fl else None})
+        roofline["frac"] = roofline["achieved"] / fp64_peak if fl else None
+    # the same two views for every kernel that has a model / an ncu count
+    kernel_rooflines = {}
+    for k, ms_k in per_launch.items():
+        if k in hbm_models and nfaces is not None:
+            kernel_rooflines[k] = {"bound": "hbm", "frac": float(hbm_models[k]()) / (ms_k * 1e-3) / 1e9 / hbm_peak}
+        elif k in ops:
+            o = ops[k]
+            kernel_rooflines[k] = {"bound": "fp64", "frac": (2.0 * o["dfma"] + o["dmul"] + o["dadd"]) / (ms_k * 1e-3) / 1e12 / fp64_peak}
+    # HBM view of the whole step (algorithmic bytes)
     hbm = {"unit": "GB/s", "peak": hbm_peak, "peak_source": hbm_src,
-           "k4_achieved": K4_ALGO_DOUBLES[D] * 8 * n_local / (k4_ms * 1e-3) / 1e9,
            "step_achieved": ALL_ALGO_BYTES[D] * n_local / (step_ms_prof * 1e-3) / 1e9}
-    hbm["k4_frac"] = hbm["k4_achieved"] / hbm_peak
     hbm["step_frac"] = hbm["step_achieved"] / hbm_peak
     kernels = {k: {"ms_per_step": v[0] / psteps, "launches_per_step": v[1] / psteps} for k, v in prof.items() if v[1]}
 
@@ -340,8 +361,8 @@ def main():
                                  % (n_local * (ALL_ALGO_BYTES[D] + 4 * (noi_mean or 32) * 4) / 1e6),
                            "parallelism": "slab%d" % world if world > 1 else "single"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "hbm_view": hbm,
-                "kernels": kernels, "cpu_baseline": cpu, "device_flags": flags}
-        print(json.dumps(line))
+                "kernel_rooflines": kernel_rooflines, "num_faces": nfaces, "kernels": kernels, "cpu_baseline": cpu, "device_flags": flags}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     gpu.close()
     if world > 1:
         dist.destroy_process_group()

@@ -161,7 +161,7 @@ int mlh_grid_info(mlh_ctx *ctx, int *cells3, double *cell_size3, double *bounds6
  * doubles: "x","y","z","vx","vy","vz","m","u","rho","P","omega","Binv"(N*D*D),
  *          "rhoGrad","vxGrad","vyGrad","vzGrad","PGrad"(N*D), "gradPre"((D+2)*N*D, debug_capture),
  *          "mF","eF"(N),"vF"(N*D) (debug_capture)
- * ints:    "cell","noi"(regular neighbours),"noiGhosts","sorted_index"
+ * ints:    "cell","noi"(regular neighbours),"noiGhosts","sorted_index","num_faces"(1 value)
  * neighbour lists: "nnl"/"nnlGhosts" -> int[N*max_interactions], row i = ORIGINAL ids of the
  *          regular neighbours (resp. parent ids of the ghost neighbours) of particle i in list
  *          order; "nnlGhostCodes" the image code of each ghost entry (2 bits/dim: 1=+L, 2=-L).

@@ -648,20 +648,44 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
         }
         int found = -1;
         unsigned m = __ballot_sync(0xffffffffu, need);
+        // four searches per pass, each reading up to 64 entries of its partner's row: eight independent loads in
+        // flight per lane instead of one dependent load -> ballot chain per search (latency-bound, profiles/r01m)
         while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int jb = __shfl_sync(0xffffffffu, j, b), wb = __shfl_sync(0xffffffffu, want, b);
-            const int tb = __shfl_sync(0xffffffffu, t0, b), te = __shfl_sync(0xffffffffu, tend, b);
-            const int *row = p.d.nnlT + (size_t)jb * p.max_ni;
-            for (int base = tb; base < te; base += 32) {
-                const int t = base + lane;
-                const bool ok = t < te && __ldg(row + t) == wb;
-                const unsigned hit = __ballot_sync(0xffffffffu, ok);
-                if (hit) {
-                    if (lane == b) found = base + __ffs(hit) - 1;
-                    break;
+            int bb[4], jb[4], wb[4], tb[4], te[4];
+            int v0[4], v1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                bb[q] = m ? __ffs(m) - 1 : -1;
+                if (m) m &= m - 1;
+                const int src = bb[q] < 0 ? 0 : bb[q];
+                jb[q] = __shfl_sync(0xffffffffu, j, src);
+                wb[q] = __shfl_sync(0xffffffffu, want, src);
+                tb[q] = __shfl_sync(0xffffffffu, t0, src);
+                te[q] = bb[q] < 0 ? 0 : __shfl_sync(0xffffffffu, tend, src);
+                if (bb[q] < 0) tb[q] = 0;
+                const int *row = p.d.nnlT + (size_t)jb[q] * p.max_ni;
+                const int t = tb[q] + lane;
+                v0[q] = t < te[q] ? __ldg(row + t) : -1;
+                v1[q] = t + 32 < te[q] ? __ldg(row + t + 32) : -1;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (bb[q] < 0) continue; // uniform
+                unsigned hit = __ballot_sync(0xffffffffu, v0[q] == wb[q]);
+                int at0 = tb[q];
+                if (!hit) {
+                    hit = __ballot_sync(0xffffffffu, v1[q] == wb[q]);
+                    at0 = tb[q] + 32;
                 }
+                if (!hit) { // rows longer than 64 entries
+                    const int *row = p.d.nnlT + (size_t)jb[q] * p.max_ni;
+                    for (int base = tb[q] + 64; base < te[q] && !hit; base += 32) {
+                        const int t = base + lane;
+                        hit = __ballot_sync(0xffffffffu, t < te[q] && __ldg(row + t) == wb[q]);
+                        at0 = base;
+                    }
+                }
+                if (hit && lane == bb[q]) found = at0 + __ffs(hit) - 1;
             }
         }
         if (need) {

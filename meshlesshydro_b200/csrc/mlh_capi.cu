@@ -857,12 +857,24 @@ __global__ void k_iota_sorted_index(const Params p, int *out) {
 extern "C" long mlh_debug_fetch(mlh_ctx *c, const char *field, void *dst, long dst_elems) {
     if (check_ctx(c) != MLH_OK || !field) return MLH_E_INVALID;
     const Params &p = c->p;
-    if (c->cfg.nranks > 1) {
-        snprintf(c->err, sizeof(c->err), "mlh_debug_fetch is single-GPU only");
-        return MLH_E_INVALID;
-    }
     const int D = p.D;
     const std::string f(field);
+    if (c->cfg.nranks > 1) {
+        // sharded runs: only per-rank statistics (device order); the per-particle harness is single-GPU
+        if (f == "noi" || f == "noiGhosts") {
+            const int n = p.own_end - p.own_begin;
+            if (p.n == 0) return MLH_E_STATE;
+            if (!dst) return n;
+            if (dst_elems < n) return MLH_E_INVALID;
+            cudaMemcpyAsync(dst, (f == "noi" ? p.d.noi : p.d.noig) + p.own_begin, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+            cudaStreamSynchronize(c->stream);
+            return n;
+        }
+        if (f != "num_faces" && f != "counters" && f != "one_sided_pairs") {
+            snprintf(c->err, sizeof(c->err), "mlh_debug_fetch(%s) is single-GPU only", field);
+            return MLH_E_INVALID;
+        }
+    }
     StateView sv = current_state(c);
     // ---- state ----
     const double *src = nullptr;
@@ -967,6 +979,13 @@ extern "C" long mlh_debug_fetch(mlh_ctx *c, const char *field, void *dst, long d
         cudaStreamSynchronize(c->stream);
         cudaFree(tmp);
         return count;
+    }
+    if (f == "num_faces") { // faces of this step's list (k_face_index)
+        if (!dst) return 1;
+        if (dst_elems < 1) return MLH_E_INVALID;
+        cudaMemcpyAsync(dst, p.d.face_start + p.own_end, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        return 1;
     }
     if (f == "one_sided_pairs" || f == "counters") {
         if (!dst) return 4;
