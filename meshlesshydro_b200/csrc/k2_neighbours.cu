@@ -79,28 +79,43 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
 
     int cnt = 0;
     bool overflow = false;
-    // ---- pass A: regular neighbours, Particles.cpp:335-359 ----
+    constexpr int NSTENCIL = D == 3 ? 27 : 9;
+    // ---- pass A: regular neighbours, Particles.cpp:335-359.  Per stencil cell the thread also records where that
+    // cell's group starts in its list (grp) and WHICH particles of the cell it lists (bit k = k-th particle of the
+    // cell): with these a partner finds its own slot in this list without a search (k_face_index, k4_flux.cu). ----
     int off[3] = {0, 0, 0};
+    int sci = -1; // stencil cell index in the reference's order
     for (off[0] = -1; off[0] <= 1; ++off[0])
         for (off[1] = -1; off[1] <= 1; ++off[1])
             for (off[2] = (D == 3 ? -1 : 0); off[2] <= (D == 3 ? 1 : 0); ++off[2]) {
+                ++sci;
+                unsigned long long mask = 0ull;
+                unsigned short g0 = (unsigned short)(cnt < p.max_ni ? cnt : p.max_ni);
                 StencilCell<D> sc = stencil_cell<D, PER>(g, ci, off);
-                if (sc.cell < 0 || sc.code != 0) continue;
-                int s = p.d.cell_start[sc.cell], e = p.d.cell_start[sc.cell + 1];
-                if (e - s > 8 * p.max_ni + 64) { overflow = true; continue; } // collapsed cell (NaN state), see k1
-                for (int j = s; j < e; ++j) {
-                    if (j == i) continue;
-                    double d[3];
+                if (sc.cell >= 0 && sc.code == 0) {
+                    int s = p.d.cell_start[sc.cell], e = p.d.cell_start[sc.cell + 1];
+                    if (e - s > 8 * p.max_ni + 64) { // collapsed cell (NaN state), see k1
+                        overflow = true;
+                        e = s;
+                    }
+                    if (e - s > 64) g0 |= 0x8000u; // more particles than mask bits: the partner searches this group
+                    for (int j = s; j < e; ++j) {
+                        if (j == i) continue;
+                        double d[3];
 #pragma unroll
-                    for (int k = 0; k < D; ++k) d[k] = __dsub_rn(p.d.x[k][j], xi[k]);
-                    if (dist_sqr_exact<D>(d) < p.hSqr) {
-                        if (cnt < p.max_ni)
-                            p.d.nnl[(size_t)cnt * p.ncap + i] = j;
-                        else
-                            overflow = true;
-                        ++cnt;
+                        for (int k = 0; k < D; ++k) d[k] = __dsub_rn(p.d.x[k][j], xi[k]);
+                        if (dist_sqr_exact<D>(d) < p.hSqr) {
+                            if (cnt < p.max_ni)
+                                p.d.nnl[(size_t)cnt * p.ncap + i] = j;
+                            else
+                                overflow = true;
+                            ++cnt;
+                            mask |= 1ull << ((j - s) & 63);
+                        }
                     }
                 }
+                p.d.grp[(size_t)sci * p.ncap + i] = g0;
+                p.d.nbm[(size_t)sci * p.ncap + i] = mask;
             }
     int nreg = cnt < p.max_ni ? cnt : p.max_ni;
     p.d.noi[i] = nreg;
@@ -168,13 +183,16 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
     // ---- face ownership: the flux pass (k4_flux.cu) evaluates every pair once, from its owner, and both endpoints
     // gather +-F.  Owner = the endpoint with the lower ORIGINAL index (the one that solves the face in the reference,
     // Particles.cpp:1841,1889); always this particle when the partner has no list on this rank (halo of another slab)
-    // or does not list the pair (one-sided periodic pair, quirk Q9).
+    // or does not list the pair (one-sided periodic pair, quirk Q9).  A regular slot owned by the partner j carries
+    // (index of i inside its cell | stencil cell of i as j sees it << 12) for k_face_index. ----
     {
         const int ntot = nreg + ng;
         const int idi = p.d.id[i];
-        int nown = 0;
+        const int li = i - p.d.cell_start[c];
+        int nown = 0, cg = 0;
         for (int s = 0; s < ntot; ++s) {
-            const int e = p.d.nnl[(size_t)s * p.ncap + i];
+            const size_t at = (size_t)s * p.ncap + i;
+            const int e = p.d.nnl[at];
             const int j = e & MLH_NNL_IDX_MASK;
             const bool canon = !(p.d.id[j] < idi);
             bool listed = true; // does j list this pair too?  (the test of pass B from j's side; exact for regular pairs)
@@ -191,9 +209,18 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
                 if (!listed) atomicAdd(&p.d.counters[0], 1u); // one-sided pair (statistics for the parity harness)
             }
             const bool own = canon || !listed || j < p.own_begin || j >= p.own_end;
-            p.d.nnlT[(size_t)i * p.max_ni + s] = e;
-            p.d.fmap[(size_t)s * p.ncap + i] = own ? (((unsigned)nown << 2) | 2u | (canon ? 0u : 1u)) : 0u;
-            nown += own ? 1 : 0;
+            unsigned v;
+            if (own) {
+                v = ((unsigned)nown << 2) | 2u | (canon ? 0u : 1u);
+                ++nown;
+            } else if (s < nreg) {
+                // stencil cell of this slot: the last group that starts at or before s
+                while (cg + 1 < NSTENCIL && (int)(p.d.grp[(size_t)(cg + 1) * p.ncap + i] & 0x7FFFu) <= s) ++cg;
+                v = ((unsigned)((li < 0xFFF ? li : 0xFFF) | ((NSTENCIL - 1 - cg) << 12))) << 2;
+            } else {
+                v = MLH_FMAP_GHOST_SEARCH;
+            }
+            p.d.fmap[at] = v;
         }
         p.d.nown[i] = nown;
     }

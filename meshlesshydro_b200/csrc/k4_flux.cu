@@ -609,24 +609,25 @@ template <int D> struct FaceRec {
 // ---------------------------------------------------------------------------------------------
 // face list: fa/fe for the owned slots, global face index for the others
 // ---------------------------------------------------------------------------------------------
-// One lane per particle; the search for a non-owned slot's face -- "where am I in my partner's list?" -- is done by
-// the whole warp: the partner's row of the particle-major list copy is read with one coalesced request and matched
-// with a ballot (a per-lane scan of the slot-major lists was L1-tag bound: 9 sectors per request, profiles/r01h).
+// Thread per particle.  Owned slots get their face number and enter the face list.  For a slot owned by the partner j,
+// K2 left (stencil cell c of this particle as j sees it, index li of this particle inside its cell): j's list is ordered
+// stencil cell by stencil cell and ascending inside a cell, so this particle sits at slot
+// grp[c][j] + popcount(nbm[c][j] & bits below li), and the face is the one j numbered for that slot -- no search.
+// [Searching j's list instead cost 0.27-0.42 ms at 61^3, L1-tag / latency bound: profiles/r01h, r01m.]  Periodic-image
+// slots (few) are found by scanning j's image entries.
 template <bool PER>
 __global__ void __launch_bounds__(128) k_face_index(const Params p) {
     const int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool active = i < p.own_end;
-    const int nreg = active ? p.d.noi[i] : 0, ntot = active ? nreg + p.d.noig[i] : 0;
-    const int fs = active ? p.d.face_start[i] : 0;
-    const int smax = __reduce_max_sync(0xffffffffu, ntot);
+    if (i >= p.own_end) return;
+    const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
+    const int fs = p.d.face_start[i];
     bool over = false;
-    for (int s = 0; s < smax; ++s) {
-        const bool has = s < ntot;
-        const size_t at = (size_t)s * p.ncap + (active ? i : p.own_begin);
-        const unsigned v = has ? p.d.fmap[at] : 2u;
-        const int e = has ? p.d.nnl[at] : 0;
-        if (has && (v & 2u)) {
+    for (int s = 0; s < ntot; ++s) {
+        const size_t at = (size_t)s * p.ncap + i;
+        const unsigned v = p.d.fmap[at];
+        const int e = p.d.nnl[at];
+        const int j = e & MLH_NNL_IDX_MASK;
+        if (v & 2u) {
             const int f = fs + (int)(v >> 2);
             if (f < p.fcap) {
                 p.d.fa[f] = i;
@@ -634,70 +635,40 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
             } else {
                 over = true;
             }
+            continue;
         }
-        // the partner owns the face: find this particle in ITS list (entry = i | reversed image code)
-        const bool need = has && !(v & 2u);
-        const int j = e & MLH_NNL_IDX_MASK;
-        const int want = i | (PER ? (reverse_code((int)((unsigned)e >> MLH_NNL_IDX_BITS)) << MLH_NNL_IDX_BITS) : 0);
-        int t0 = 0, tend = 0;
-        if (need) {
+        int t = -1;
+        if (!PER || s < nreg) {
+            const int li = (int)((v >> 2) & 0xFFFu), c = (int)(v >> 14);
+            const unsigned g0 = p.d.grp[(size_t)c * p.ncap + j];
             const int nrj = p.d.noi[j];
-            const bool ghost = PER && s >= nreg;
-            t0 = ghost ? nrj : 0;
-            tend = ghost ? nrj + p.d.noig[j] : nrj;
-        }
-        int found = -1;
-        unsigned m = __ballot_sync(0xffffffffu, need);
-        // four searches per pass, each reading up to 64 entries of its partner's row: eight independent loads in
-        // flight per lane instead of one dependent load -> ballot chain per search (latency-bound, profiles/r01m)
-        while (m) {
-            int bb[4], jb[4], wb[4], tb[4], te[4];
-            int v0[4], v1[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                bb[q] = m ? __ffs(m) - 1 : -1;
-                if (m) m &= m - 1;
-                const int src = bb[q] < 0 ? 0 : bb[q];
-                jb[q] = __shfl_sync(0xffffffffu, j, src);
-                wb[q] = __shfl_sync(0xffffffffu, want, src);
-                tb[q] = __shfl_sync(0xffffffffu, t0, src);
-                te[q] = bb[q] < 0 ? 0 : __shfl_sync(0xffffffffu, tend, src);
-                if (bb[q] < 0) tb[q] = 0;
-                const int *row = p.d.nnlT + (size_t)jb[q] * p.max_ni;
-                const int t = tb[q] + lane;
-                v0[q] = t < te[q] ? __ldg(row + t) : -1;
-                v1[q] = t + 32 < te[q] ? __ldg(row + t + 32) : -1;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (bb[q] < 0) continue; // uniform
-                unsigned hit = __ballot_sync(0xffffffffu, v0[q] == wb[q]);
-                int at0 = tb[q];
-                if (!hit) {
-                    hit = __ballot_sync(0xffffffffu, v1[q] == wb[q]);
-                    at0 = tb[q] + 32;
-                }
-                if (!hit) { // rows longer than 64 entries
-                    const int *row = p.d.nnlT + (size_t)jb[q] * p.max_ni;
-                    for (int base = tb[q] + 64; base < te[q] && !hit; base += 32) {
-                        const int t = base + lane;
-                        hit = __ballot_sync(0xffffffffu, t < te[q] && __ldg(row + t) == wb[q]);
-                        at0 = base;
+            if (!(g0 & 0x8000u) && li < 64) {
+                t = (int)g0 + __popcll(p.d.nbm[(size_t)c * p.ncap + j] & ((1ull << li) - 1ull));
+                if (t >= nrj || p.d.nnl[(size_t)t * p.ncap + j] != i) t = -1; // j's list was cut at max_interactions
+            } else { // crowded cell: scan j's list from the start of the group
+                for (int q = (int)(g0 & 0x7FFFu); q < nrj; ++q)
+                    if (p.d.nnl[(size_t)q * p.ncap + j] == i) {
+                        t = q;
+                        break;
                     }
+            }
+        } else {
+            const int want = i | (reverse_code((int)((unsigned)e >> MLH_NNL_IDX_BITS)) << MLH_NNL_IDX_BITS);
+            const int nrj = p.d.noi[j], ntj = nrj + p.d.noig[j];
+            for (int q = nrj; q < ntj; ++q)
+                if (p.d.nnl[(size_t)q * p.ncap + j] == want) {
+                    t = q;
+                    break;
                 }
-                if (hit && lane == bb[q]) found = at0 + __ffs(hit) - 1;
-            }
         }
-        if (need) {
-            unsigned res = MLH_FMAP_SKIP;
-            if (found >= 0) {
-                const unsigned vj = p.d.fmap[(size_t)found * p.ncap + j]; // owned by j: rank << 2 | 2 | sign
-                res = ((unsigned)(p.d.face_start[j] + (int)(vj >> 2)) << 2) | 1u;
-            } else {
-                over = true; // j's list overflowed (MLH_F_MAX_INTERACTIONS is raised by K2 as well)
-            }
-            p.d.fmap[at] = res;
+        unsigned res = MLH_FMAP_SKIP;
+        if (t >= 0) {
+            const unsigned vj = p.d.fmap[(size_t)t * p.ncap + j]; // owned by j: rank << 2 | 2 | sign
+            res = ((unsigned)(p.d.face_start[j] + (int)(vj >> 2)) << 2) | 1u;
+        } else {
+            over = true; // (MLH_F_MAX_INTERACTIONS is raised by K2 as well)
         }
+        p.d.fmap[at] = res;
     }
     if (over) atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
 }

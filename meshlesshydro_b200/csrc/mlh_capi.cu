@@ -87,7 +87,8 @@ static void carve_pool(mlh_ctx *c, Carver &cv) {
     d.ckey = cv.take<int>(n); d.crank = cv.take<int>(n); d.perm = cv.take<int>(n);
     d.nnl = cv.take<int>(n * (size_t)p.max_ni);
     d.fmap = cv.take<unsigned>(n * (size_t)p.max_ni);
-    d.nnlT = cv.take<int>(n * (size_t)p.max_ni);
+    d.grp = cv.take<unsigned short>(n * (size_t)27);
+    d.nbm = cv.take<unsigned long long>(n * (size_t)27);
     d.nown = cv.take<int>(n);
     d.face_start = cv.take<int>(n + 1);
     d.face_scan_tmp = cv.take<int>(n / 1024 + 4);

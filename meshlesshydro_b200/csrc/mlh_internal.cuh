@@ -16,7 +16,8 @@
 //            another rank or does not list the pair, quirk Q9).  fmap (slot-major like nnl) maps
 //            each list slot to its face: bits [2..31] value, bit 1 = owned (value = rank among the
 //            owner's owned slots, face index = face_start[i] + rank), else value = global face
-//            index; bit 0 = this endpoint adds -F.  fa/fe = owner index and list entry of face f;
+//            index; bit 0 = this endpoint adds -F.  Between K2 and k_face_index a partner-owned slot holds
+//            (index of the particle inside its own cell | mirrored stencil cell << 12).  fa/fe = owner index and list entry of face f;
 //            F = fluxes in canonical orientation, AoS MLH_FREC(D) doubles per face.
 #pragma once
 #include <cuda_runtime.h>
@@ -31,6 +32,7 @@
 #define MLH_NNL_IDX_MASK ((1 << MLH_NNL_IDX_BITS) - 1)
 #define MLH_FREC(D) ((D) == 2 ? 4 : 6)      // doubles per face in the flux array (D+2 used)
 #define MLH_FMAP_SKIP 0xFFFFFFFCu           // slot without a face (partner's list overflowed)
+#define MLH_FMAP_GHOST_SEARCH 0xFFFFFFF8u    // K2 -> k_face_index: periodic-image slot owned by the partner (searched)
 
 // constants of the restated exact Riemann solver (same expressions as oracle/riemann_exact.h:rs_init)
 struct RsConsts {
@@ -55,7 +57,8 @@ struct DevPtrs {
     double *B[9];   // Binv row-major as used by the reference (Particles.cpp:1249)
     double *g[15];  // gradients: field f in {0 rho,1 vx,2 vy,3 vz,4 P}; component a -> g[f*3+a]
     int *id, *cell, *noi, *noig, *nnl;
-    int *nnlT;      // particle-major copy of nnl (row i at nnlT[i*max_ni ..]): k_face_index searches partners' rows
+    unsigned short *grp; // grp[c*ncap + i] = first slot of stencil cell c (reference order) in the list of i (bit 15: cell holds > 64 particles)
+    unsigned long long *nbm; // nbm[c*ncap + i] bit k = i lists the k-th particle of stencil cell c
     // faces (see header comment)
     unsigned *fmap;
     int *nown, *face_start, *face_scan_tmp, *fa, *fe;
