@@ -36,7 +36,7 @@ __device__ __forceinline__ void load_neighbour(const Params &p, int e, double *n
 }
 
 template <int D, bool PER>
-__global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
+__global__ void __launch_bounds__(128, 4) k_gradient_limit(const Params p) {
     constexpr int NF = D + 2;
     constexpr int PK1 = MLH_PK1(D);
     int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,9 +68,14 @@ __global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
 #pragma unroll
             for (int a = 0; a < D; ++a) g[f][a] = 0.;
 
-        // ---- sweep 1: gradients ----
+        // ---- sweep 1: gradients + signal velocity (compGlobalTimestep, Particles.cpp:1446-1485: regular entries only,
+        // quirk Q7; it needs the same |x_i - x_j| as the kernel weight, so it rides along here) ----
+        double vSig = DBL_MIN; // quirk Q2
+        const double ci = own[2 * D + 2];
+        int e_next = ntot > 0 ? p.d.nnl[i] : 0; // list entries are fetched one visit ahead of the record gather
         for (int s = 0; s < ntot; ++s) {
-            const int e = p.d.nnl[(size_t)s * p.ncap + i];
+            const int e = e_next;
+            if (s + 1 < ntot) e_next = p.d.nnl[(size_t)(s + 1) * p.ncap + i];
             double nb[PK1];
             load_neighbour<D, PER>(p, e, nb);
             double d[3], sd[3];
@@ -95,6 +100,16 @@ __global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
 #pragma unroll
                 for (int a = 0; a < D; ++a) g[f][a] = __dadd_rn(g[f][a], __dmul_rn(df, pt[a]));
             }
+            if (s < nreg) {
+                // xij = x_i - x_j = sd, and sqrt(dotProduct(xij, xij)) is r bit for bit (same products, same sum order)
+                double vij[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) vij[k] = __dsub_rn(own[D + k], nb[D + k]);
+                double vijxij = __ddiv_rn(dot_seq<D>(vij, sd), r);
+                vijxij = vijxij < 0. ? vijxij : 0.;
+                const double vSig_i = __dsub_rn(__dadd_rn(ci, nb[2 * D + 2]), vijxij);
+                vSig = vSig_i > vSig ? vSig_i : vSig;
+            }
         }
         if (p.debug_capture) {
 #pragma unroll
@@ -103,7 +118,7 @@ __global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
                 for (int a = 0; a < D; ++a) p.d.gpre[fslot[f] * 3 + a][i] = g[f][a];
         }
 
-        // ---- sweep 2: slope limiter extrema (all entries) + signal velocity (regular entries only, quirk Q7) ----
+        // ---- sweep 2: slope limiter extrema (all entries) ----
         double maxNgb[NF], minNgb[NF], maxMid[NF], minMid[NF];
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
@@ -112,17 +127,17 @@ __global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
             maxMid[f] = DBL_MIN;
             minMid[f] = DBL_MAX;
         }
-        double vSig = DBL_MIN; // quirk Q2
-        const double ci = own[2 * D + 2];
-        for (int s = 0; s < ntot; ++s) {
-            const int e = p.d.nnl[(size_t)s * p.ncap + i];
+        e_next = ntot > 0 ? p.d.nnl[i] : 0;
+        for (int s = 0; p.slope_limiting && s < ntot; ++s) {
+            const int e = e_next;
+            if (s + 1 < ntot) e_next = p.d.nnl[(size_t)(s + 1) * p.ncap + i];
             double nb[PK1];
             load_neighbour<D, PER>(p, e, nb);
-            if (p.slope_limiting) {
+            {
                 double xijxi[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    const double xij = __ddiv_rn(__dadd_rn(xi[k], nb[k]), 2.); // FIRST_ORDER_QUAD_POINT, :1355-1356
+                    const double xij = __dmul_rn(__dadd_rn(xi[k], nb[k]), .5); // (x_i + x_j)/2 (exact either way), FIRST_ORDER_QUAD_POINT, :1355-1356
                     xijxi[k] = __dsub_rn(xij, xi[k]);
                 }
 #pragma unroll
@@ -134,18 +149,6 @@ __global__ void __launch_bounds__(128) k_gradient_limit(const Params p) {
                     if (maxMid[f] < fij) maxMid[f] = fij;
                     if (minMid[f] > fij) minMid[f] = fij;
                 }
-            }
-            if (s < nreg) { // compGlobalTimestep, Particles.cpp:1446-1485
-                double xij[D], vij[D];
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    xij[k] = __dsub_rn(xi[k], nb[k]);
-                    vij[k] = __dsub_rn(own[D + k], nb[D + k]);
-                }
-                double vijxij = __ddiv_rn(dot_seq<D>(vij, xij), sqrt(dot_seq<D>(xij, xij)));
-                vijxij = vijxij < 0. ? vijxij : 0.;
-                const double vSig_i = __dsub_rn(__dadd_rn(ci, nb[2 * D + 2]), vijxij);
-                vSig = vSig_i > vSig ? vSig_i : vSig;
             }
         }
         if (p.slope_limiting) {

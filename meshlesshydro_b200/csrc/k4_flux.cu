@@ -136,6 +136,7 @@ __device__ __noinline__ double rs_guess_nonlinear(const RsConsts c, double rhoL,
 struct RsProblem {
     double rhoL, PL, aL, rhoR, PR, aR, du; // du = uR - uL
     double Pguess, fPguess, f0, fpsum;     // f(Pguess), f(0), fL'(Pguess) + fR'(Pguess)
+    double iPL, iPR;                       // 1/PL, 1/PR (k_face_iterate only: one division per face instead of one per iteration)
 };
 
 // Root finder as a resumable state machine: one call of rs_iter_step() = one new trial pressure + one
@@ -251,7 +252,7 @@ __device__ __forceinline__ void rs_iter_update(RsIter &it, double s, double fs, 
 // both kinds anyway, so the divergent version executed all four paths with half-empty warps (profiles/r01k); here the
 // two sides are independent instruction streams that overlap in the FP64 pipe.
 __device__ __forceinline__ double rs_f_nobranch(const RsConsts &c, const RsProblem &q, double Ps) {
-    const double wL = rs_root_pow(c, Ps / q.PL), wR = rs_root_pow(c, Ps / q.PR);
+    const double wL = rs_root_pow(c, Ps * q.iPL), wR = rs_root_pow(c, Ps * q.iPR);
     const double qL = c.sqrt_tdgp1 * rsqrt(q.rhoL * (Ps + c.gm1dgp1 * q.PL));
     const double qR = c.sqrt_tdgp1 * rsqrt(q.rhoR * (Ps + c.gm1dgp1 * q.PR));
     const double fL = (Ps > q.PL) ? (Ps - q.PL) * qL : c.tdgm1 * q.aL * (wL - 1.);
@@ -435,38 +436,42 @@ __device__ __forceinline__ int rs_sample(const RsConsts &c, const RsProblem &q, 
 // ---------------------------------------------------------------------------------------------
 // Particles::pairwiseLimiter, Particles.cpp:1735-1785 (quirk Q1)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double pairwise_limiter(const Params &p, double phi0, double phi_i, double phi_j,
-                                                   double xijxi_abs, double xjxi_abs) {
+// Both endpoints of a face call the limiter with (phi_i, phi_j) swapped: phiMin/phiMax, delta1/delta2 and phiPlus/phiMinus
+// are the same values for the two calls (|phi_i - phi_j| is symmetric in either abs mode), so they are computed once
+// per component (PairLimits) and each side only does its own selection -- same expressions, same results.
+struct PairLimits {
+    double delta2, phiPlus, phiMinus;
+};
+__device__ __forceinline__ PairLimits pairwise_limits(const Params &p, double phi_i, double phi_j) {
     const int am = p.abs_mode;
-    double phi_ = phi_i;
-    double phi_ij = phi_i + xijxi_abs / xjxi_abs * (phi_j - phi_i);
-    double phiMin, phiMax;
-    if (phi_i < phi_j) {
-        phiMin = phi_i;
-        phiMax = phi_j;
-    } else {
-        phiMin = phi_j;
-        phiMax = phi_i;
-    }
-    double delta1 = p.psi1 * q1_abs(phi_i - phi_j, am);
-    double delta2 = p.psi2 * q1_abs(phi_i - phi_j, am);
-    double phiMinus, phiPlus;
+    const bool lt = phi_i < phi_j;
+    const double phiMin = lt ? phi_i : phi_j, phiMax = lt ? phi_j : phi_i;
+    const double ad = q1_abs(phi_i - phi_j, am);
+    const double delta1 = p.psi1 * ad;
+    PairLimits r;
+    r.delta2 = p.psi2 * ad;
     if ((phiMax + delta1 >= 0. && phiMax >= 0.) || (phiMax + delta1 < 0. && phiMax < 0.)) {
-        phiPlus = phiMax + delta1;
+        r.phiPlus = phiMax + delta1;
     } else {
-        phiPlus = phiMax / (1. + delta1 / q1_abs(phiMax, am));
+        r.phiPlus = phiMax / (1. + delta1 / q1_abs(phiMax, am));
     }
     if ((phiMin - delta1 >= 0. && phiMin >= 0.) || (phiMin - delta1 < 0. && phiMin < 0.)) {
-        phiMinus = phiMin - delta1;
+        r.phiMinus = phiMin - delta1;
     } else {
-        phiMinus = phiMin / (1. + delta1 / q1_abs(phiMin, am));
+        r.phiMinus = phiMin / (1. + delta1 / q1_abs(phiMin, am));
     }
+    return r;
+}
+// ratio = |x_ij - x_i| / |x_j - x_i| (evaluated once per side: `xijxi_abs / xjxi_abs * (phi_j - phi_i)` is left-associative)
+__device__ __forceinline__ double pairwise_limiter(const PairLimits &l, double phi0, double phi_i, double phi_j, double ratio) {
+    double phi_ = phi_i;
+    const double phi_ij = phi_i + ratio * (phi_j - phi_i);
     if (phi_i < phi_j) {
-        double minPhiD2 = (phi_ij + delta2 < phi0) ? phi_ij + delta2 : phi0;
-        phi_ = phiMinus > minPhiD2 ? phiMinus : minPhiD2;
+        const double minPhiD2 = (phi_ij + l.delta2 < phi0) ? phi_ij + l.delta2 : phi0;
+        phi_ = l.phiMinus > minPhiD2 ? l.phiMinus : minPhiD2;
     } else if (phi_i > phi_j) {
-        double maxPhiD2 = (phi_ij - delta2 > phi0) ? phi_ij - delta2 : phi0;
-        phi_ = phiPlus < maxPhiD2 ? phiPlus : maxPhiD2;
+        const double maxPhiD2 = (phi_ij - l.delta2 > phi0) ? phi_ij - l.delta2 : phi0;
+        phi_ = l.phiPlus < maxPhiD2 ? l.phiPlus : maxPhiD2;
     }
     return phi_;
 }
@@ -630,7 +635,7 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
         if (v & 2u) {
             const int f = fs + (int)(v >> 2);
             if (f < p.fcap) {
-                p.d.fa[f] = i;
+                p.d.fa[f] = i | (int)((v & 1u) << 31); // bit 31: the partner is the canonical endpoint (lower original index)
                 p.d.fe[f] = e;
             } else {
                 over = true;
@@ -689,13 +694,14 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
     const double dt = *p.d.dt_used;
     const double gamma = p.gamma;
     for (int f = f0 + blockIdx.x * MLH_FACE_TILE + threadIdx.x; f < f1; f += gridDim.x * MLH_FACE_TILE) {
-        const int i = p.d.fa[f];
+        const int fav = p.d.fa[f];
+        const int i = fav & 0x7FFFFFFF;
         const int e = p.d.fe[f];
         const int j = e & MLH_NNL_IDX_MASK;
         const int code = PER ? (int)((unsigned)e >> MLH_NNL_IDX_BITS) : 0;
-        const int ids = p.d.id[i], idn = p.d.id[j];
-        // canonical orientation: the endpoint with the lower ORIGINAL index plays "i" (Particles.cpp:1841,1889)
-        const bool canon = !(idn < ids);
+        // canonical orientation: the endpoint with the lower ORIGINAL index plays "i" (Particles.cpp:1841,1889);
+        // K2 compared the ids when it marked the owner, k_face_index passed the result on in bit 31 of fa
+        const bool canon = fav >= 0;
         const int ia = canon ? i : j, ib = canon ? j : i; // a = canonical endpoint, b = the other
         double A1[PK1], B1[PK1]; // packed records: x, v, rho, P, cs, omega
         load_packed<PK1>(p.d.pk1 + (size_t)ia * PK1, A1);
@@ -737,7 +743,8 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
             const double r2 = (PER && code != 0) ? sqrt(dist_sqr_exact<D>(s2)) : r1;
             const double w1 = cubic_spline(r1, p);
             const double w2 = (PER && code != 0) ? cubic_spline(r2, p) : w1;
-            const double psi1 = w1 / omga, psi2 = w2 / omgb;
+            const double ioa = 1. / omga, iob = 1. / omgb;
+            const double psi1 = w1 * ioa, psi2 = w2 * iob;
             double A2[PK2], B2[PK2]; // packed records: Binv, limited gradients (W order)
             load_packed<PK2>(p.d.pk2 + (size_t)ia * PK2, A2);
             load_packed<PK2>(p.d.pk2 + (size_t)ib * PK2, B2);
@@ -749,7 +756,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
                     t1 += A2[D * al + be] * d1[be] * psi1;
                     t2 += B2[D * al + be] * d2[be] * psi2;
                 }
-                A[al] = 1. / omga * t1 - 1. / omgb * t2;
+                A[al] = ioa * t1 - iob * t2;
             }
 #pragma unroll
             for (int nu = 0; nu < NW; ++nu)
@@ -801,10 +808,12 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
             na = sqrt(na);
             nb = sqrt(nb);
             nab = sqrt(nab);
+            const double ra = na / nab, rb = nb / nab;
 #pragma unroll
             for (int nu = 0; nu < NW; ++nu) {
-                const double wa = pairwise_limiter(p, Wa[nu], Wa0[nu], Wb0[nu], na, nab);
-                const double wb = pairwise_limiter(p, Wb[nu], Wb0[nu], Wa0[nu], nb, nab);
+                const PairLimits lim = pairwise_limits(p, Wa0[nu], Wb0[nu]);
+                const double wa = pairwise_limiter(lim, Wa[nu], Wa0[nu], Wb0[nu], ra);
+                const double wb = pairwise_limiter(lim, Wb[nu], Wb0[nu], Wa0[nu], rb);
                 Wa[nu] = wa;
                 Wb[nu] = wb;
             }
@@ -819,27 +828,31 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
             }
             const double wa0 = va[0] - vF[0], wa1 = va[1] - vF[1];
             const double wb0 = vb[0] - vF[0], wb1 = vb[1] - vF[1];
-            Wa[0] -= dt / 2. * (rhoa * aDiv + wa0 * ga[0][0] + wa1 * ga[0][1]);
-            Wb[0] -= dt / 2. * (rhob * bDiv + wb0 * gb[0][0] + wb1 * gb[0][1]);
-            Wa[1] -= dt / 2. * (gamma * Pa * aDiv + wa0 * ga[1][0] + wa1 * ga[1][1]);
-            Wb[1] -= dt / 2. * (gamma * Pb * bDiv + wb0 * gb[1][0] + wb1 * gb[1][1]);
-            Wa[2] -= dt / 2. * (ga[1][0] / rhoa + wa0 * ga[2][0] + wa1 * ga[2][1]);
-            Wb[2] -= dt / 2. * (gb[1][0] / rhob + wb0 * gb[2][0] + wb1 * gb[2][1]);
-            Wa[3] -= dt / 2. * (ga[1][1] / rhoa + wa0 * ga[3][0] + wa1 * ga[3][1]);
-            Wb[3] -= dt / 2. * (gb[1][1] / rhob + wb0 * gb[3][0] + wb1 * gb[3][1]);
+            // grad P / rho as a product with 1/rho: limited gradients are very often exactly 0, and 0/rho takes the
+            // ~60-instruction special-operand path of the FP64 division (15 % of this kernel's instructions, profiles/r01o)
+            const double ira = 1. / rhoa, irb = 1. / rhob;
+            const double hdt = dt / 2.;
+            Wa[0] -= hdt * (rhoa * aDiv + wa0 * ga[0][0] + wa1 * ga[0][1]);
+            Wb[0] -= hdt * (rhob * bDiv + wb0 * gb[0][0] + wb1 * gb[0][1]);
+            Wa[1] -= hdt * (gamma * Pa * aDiv + wa0 * ga[1][0] + wa1 * ga[1][1]);
+            Wb[1] -= hdt * (gamma * Pb * bDiv + wb0 * gb[1][0] + wb1 * gb[1][1]);
+            Wa[2] -= hdt * (ga[1][0] * ira + wa0 * ga[2][0] + wa1 * ga[2][1]);
+            Wb[2] -= hdt * (gb[1][0] * irb + wb0 * gb[2][0] + wb1 * gb[2][1]);
+            Wa[3] -= hdt * (ga[1][1] * ira + wa0 * ga[3][0] + wa1 * ga[3][1]);
+            Wb[3] -= hdt * (gb[1][1] * irb + wb0 * gb[3][0] + wb1 * gb[3][1]);
             if (D == 3) {
                 const double wa2 = va[D - 1] - vF[D - 1], wb2 = vb[D - 1] - vF[D - 1];
                 const double wq3 = (p.q3_mode == MLH_Q3_FIXED) ? wb2 : wa2; // quirk Q3 (:1717,:1719)
-                Wa[0] -= dt / 2. * wa2 * ga[0][D - 1];
-                Wb[0] -= dt / 2. * wb2 * gb[0][D - 1];
-                Wa[1] -= dt / 2. * wa2 * ga[1][D - 1];
-                Wb[1] -= dt / 2. * wb2 * gb[1][D - 1];
-                Wa[2] -= dt / 2. * wa2 * ga[2][D - 1];
-                Wb[2] -= dt / 2. * wq3 * gb[2][D - 1];
-                Wa[3] -= dt / 2. * wa2 * ga[3][D - 1];
-                Wb[3] -= dt / 2. * wq3 * gb[3][D - 1];
-                Wa[NW - 1] -= dt / 2. * (ga[1][D - 1] / rhoa + wa0 * ga[NW - 1][0] + wa1 * ga[NW - 1][1] + wa2 * ga[NW - 1][D - 1]);
-                Wb[NW - 1] -= dt / 2. * (gb[1][D - 1] / rhob + wb0 * gb[NW - 1][0] + wb1 * gb[NW - 1][1] + wb2 * gb[NW - 1][D - 1]);
+                Wa[0] -= hdt * wa2 * ga[0][D - 1];
+                Wb[0] -= hdt * wb2 * gb[0][D - 1];
+                Wa[1] -= hdt * wa2 * ga[1][D - 1];
+                Wb[1] -= hdt * wb2 * gb[1][D - 1];
+                Wa[2] -= hdt * wa2 * ga[2][D - 1];
+                Wb[2] -= hdt * wq3 * gb[2][D - 1];
+                Wa[3] -= hdt * wa2 * ga[3][D - 1];
+                Wb[3] -= hdt * wq3 * gb[3][D - 1];
+                Wa[NW - 1] -= hdt * (ga[1][D - 1] * ira + wa0 * ga[NW - 1][0] + wa1 * ga[NW - 1][1] + wa2 * ga[NW - 1][D - 1]);
+                Wb[NW - 1] -= hdt * (gb[1][D - 1] * irb + wb0 * gb[NW - 1][0] + wb1 * gb[NW - 1][1] + wb2 * gb[NW - 1][D - 1]);
             }
         }
         if (PER && code != 0 && (Wa[1] < 0. || Wb[1] < 0.)) atomicOr(p.d.flags, MLH_F_NEG_GHOST_PRESSURE);
@@ -1002,6 +1015,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_i
     RsProblem q;
     q.rhoL = q.PL = q.aL = q.rhoR = q.PR = q.aR = 1.;
     q.du = q.Pguess = q.fPguess = q.f0 = q.fpsum = 0.;
+    q.iPL = q.iPR = 1.;
     RsIter it;
     it.method = RS_DONE;
     it.mflag = 0;
@@ -1049,6 +1063,8 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_i
                 const int slot = (head + rank) & (MLH_RING - 1);
                 q.rhoL = rd[0][slot]; q.PL = rd[1][slot]; q.aL = rd[2][slot]; q.rhoR = rd[3][slot]; q.PR = rd[4][slot];
                 q.aR = rd[5][slot]; q.du = rd[6][slot];
+                q.iPL = 1. / q.PL;
+                q.iPR = 1. / q.PR;
                 const double v0 = rd[7][slot], v1 = rd[8][slot], v2 = rd[9][slot], v3 = rd[10][slot];
                 face = ri[slot];
                 const bool nw = rk[slot] == RS_NEWTON;

@@ -157,11 +157,10 @@ __device__ __forceinline__ int reverse_code(int code) {
 // quirk Q1: `abs` at Particles.cpp:1416-1417,1748-1759
 __device__ __forceinline__ double q1_abs(double v, int mode) {
     if (mode == MLH_ABS_FABS) return fabs(v);
-    int k;
-    if (!(v > -2147483649.0 && v < 2147483648.0))
-        k = INT_MIN; // x86-64 cvttsd2si "integer indefinite"
-    else
-        k = (int)v;  // truncation toward zero
+    // x86-64 cvttsd2si: truncation toward zero; NaN and anything outside int32 give the "integer indefinite" INT_MIN.
+    // cvt.rzi.s32.f64 saturates instead (NaN -> 0, v >= 2^31 -> INT_MAX, v <= -2^31 -> INT_MIN): patch the first two.
+    int k = __double2int_rz(v);
+    if (!(v < 2147483648.0)) k = INT_MIN;
     if (k < 0) k = (int)(0u - (unsigned)k);
     return (double)k;
 }
@@ -194,7 +193,7 @@ __device__ __forceinline__ void neighbour_geometry(const Params &p, const double
     double s[3];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        double xj = p.d.x[k][j];
+        double xj = p.d.x[k][j]; // SoA on purpose: the neighbours of one stencil cell are consecutive j, i.e. 4 per sector
         if (PER) {
             int ck = (e >> (MLH_NNL_IDX_BITS + 2 * k)) & 3;
             xj = image_coord(xj, ck, p.grid.bmin[k], p.grid.bmax[k]);

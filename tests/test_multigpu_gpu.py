@@ -16,12 +16,14 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("case,steps", [("kh", 4), ("sedov", 3), ("fb", 3)])
-def test_two_ranks_bitwise_equal_single_gpu(case, steps):
-    if _ngpu() < 2:
-        pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", os.path.join(ROOT, "tests", "mgpu_worker.py"), case, str(steps)]
+def test_ranks_bitwise_equal_single_gpu(case, steps, world):
+    """world = 4 adds what 2 ranks cannot show: interior slabs with two distinct neighbours"""
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
+           "--master-port", str(29611 + world), os.path.join(ROOT, "tests", "mgpu_worker.py"), case, str(steps)]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:]
