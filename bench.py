@@ -208,9 +208,11 @@ def main():
                            q13_mode=capi.Q13_ZERO_Z, max_interactions=128 if D == 3 else 96)
     cfg.device = local_rank
     cfg.rank, cfg.nranks = rank, world
+    ids_local = None
     if world > 1:
         from meshlesshydro_b200 import multigpu
         gpu, ic_local = multigpu.create_sharded(cfg, ic, dist)
+        ids_local = multigpu.shard(ic, rank, world)[1]
     else:
         gpu, ic_local = capi.MfvGpu(cfg), ic
         gpu.upload(ic_local)
@@ -320,32 +322,40 @@ def main():
 
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
+        # every rank: H2D of its shard from pinned host arrays, one step, D2H of the result.  Single GPU: the next step
+        # starts from the downloaded state (host round trip).  Sharded: particles migrate between slabs, so the owned set
+        # a rank downloads may differ from the one it uploaded; every step therefore uploads the rank's initial shard
+        # (same bytes, same work) and the download buffers are sized for the largest owned set.
         names = ["x", "y", "vx", "vy", "m", "u"] + (["z", "vz"] if D == 3 else [])
         host = {k: capi.pinned_empty(n_local) for k in names}
         for k in names:
             host[k][:] = ic_local[k]
         host_ic = dict(ic_local)
         host_ic.update(host)
-        out = {k: (capi.pinned_empty(n_local) if k in names else None) for k in ["x", "y", "z", "vx", "vy", "vz", "m", "u"]}
-        out["ids"] = capi.pinned_empty(n_local, np.int32)
+        n_out = n_local if world == 1 else int(cfg.capacity)
+        out = {k: (capi.pinned_empty(n_out) if k in names else None) for k in ["x", "y", "z", "vx", "vy", "vz", "m", "u"]}
+        out["ids"] = capi.pinned_empty(n_out, np.int32)
         esteps = max(3, min(args.steps, 10))
         for _ in range(2):
-            gpu.upload(host_ic)
+            gpu.upload(host_ic, ids=ids_local)
             gpu.step(want_dt=False)
             gpu.download_state(out)
-        gpu.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(esteps):
-            gpu.upload(host_ic)           # H2D of this step's inputs
+            gpu.upload(host_ic, ids=ids_local)  # H2D of this step's inputs
             gpu.step(want_dt=False)
-            gpu.download_state(out)       # D2H of the step's result (synchronises)
-            for k in names:               # next step starts from the downloaded state (host round trip)
-                host[k][:] = out[k]
-        e_s = time.perf_counter() - t0
+            gpu.download_state(out)             # D2H of the step's result (synchronises)
+            if world == 1:
+                for k in names:                 # next step starts from the downloaded state (host round trip)
+                    host[k][:] = out[k]
+        barrier()
+        e_s = max_over_ranks(time.perf_counter() - t0)
         nb = len(names) * 8 * n_local
         e2e = {"value": n_total * esteps / e_s, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb + 4 * n_local,
-               "steps": esteps, "ms_per_step": 1e3 * e_s / esteps, "timing": "host wall clock around upload+step+download, pinned buffers"}
+               "steps": esteps, "ms_per_step": 1e3 * e_s / esteps,
+               "timing": "host wall clock (max over ranks) around upload+step+download, pinned buffers; bytes are rank 0's"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         side = {"sedov61": 61, "sedov128": 61, "sedov256": 61, "kh100": 100, "kh1000": 200, "kh2000": 200, "fb1000": 200}[wname]

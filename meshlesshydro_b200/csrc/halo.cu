@@ -211,8 +211,10 @@ int mlh_comm_bbox(mlh_ctx *c) {
     }
     double *b = c->p.d.bbox;
     MLH_NCCL_CHECK(c, g_nccl.GroupStart());
-    MLH_NCCL_CHECK(c, g_nccl.AllReduce(b, b, 3, ncclDouble, ncclMin, comm, c->stream));
-    MLH_NCCL_CHECK(c, g_nccl.AllReduce(b + 3, b + 3, 6, ncclDouble, ncclMax, comm, c->stream));
+    // [0..5] are order-preserving keys (dbl_key): min / max of the keys == key of the min / max
+    MLH_NCCL_CHECK(c, g_nccl.AllReduce(b, b, 3, ncclUint64, ncclMin, comm, c->stream));
+    MLH_NCCL_CHECK(c, g_nccl.AllReduce(b + 3, b + 3, 3, ncclUint64, ncclMax, comm, c->stream));
+    MLH_NCCL_CHECK(c, g_nccl.AllReduce(b + 6, b + 6, 3, ncclDouble, ncclMax, comm, c->stream));
     MLH_NCCL_CHECK(c, g_nccl.GroupEnd());
     c->launches += 1;
     return MLH_OK;

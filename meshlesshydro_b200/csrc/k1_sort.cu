@@ -133,38 +133,30 @@ __global__ void __launch_bounds__(256) k_scatter_perm(const Params p) {
     p.d.perm[p.d.cell_start[p.d.ckey[i]] + p.d.crank[i]] = i;
 }
 
-// canonical order inside a cell: ascending original index (one thread per cell, insertion sort;
-// cells hold O(10) particles because cellSize >= h, Domain.cpp:10-22)
-__global__ void __launch_bounds__(128) k_sort_within_cells(const Params p) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= p.grid.ncells) return;
-    int s = p.d.cell_start[c], e = p.d.cell_start[c + 1];
-    if (e - s > 8 * p.max_ni + 64) {
-        // far more particles in one cell (edge >= h) than any neighbour list can hold: the search would
-        // overflow MAX_NUM_INTERACTIONS anyway (reference: exit(1)); typical cause is a NaN state collapsing
-        // into one cell.  Raise the flag instead of spending O(n^2) here.
-        atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
-        return;
-    }
-    for (int a = s + 1; a < e; ++a) {
-        int pa = p.d.perm[a];
-        int ka = p.d.cid[pa];
-        int b = a - 1;
-        while (b >= s) {
-            int pb = p.d.perm[b];
-            if (p.d.cid[pb] <= ka) break;
-            p.d.perm[b + 1] = pb;
-            --b;
-        }
-        p.d.perm[b + 1] = pa;
-    }
-}
-
+// Reorder into cell order.  perm (k_scatter_perm) lists the members of a cell in arrival order of the atomics; the
+// canonical order inside a cell is ascending ORIGINAL index (Cell::prtcls push_back order, Particles.cpp:319).  Cells
+// hold O(10) particles because cellSize >= h (Domain.cpp:10-22), so every particle simply counts the members of its
+// cell with a smaller id -- independent loads, one thread per particle -- and writes itself to cell_start + rank.
+// [A separate one-thread-per-cell insertion sort took 37 us at 61^3 for 22k threads of dependent loads: profiles/r01o.]
 template <int D>
 __global__ void __launch_bounds__(256) k_gather_sorted(const Params p) {
-    int dst = blockIdx.x * blockDim.x + threadIdx.x;
-    if (dst >= p.ncur) return;
-    int src = p.d.perm[dst];
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= p.ncur) return;
+    const int src = p.d.perm[a];
+    const int id = p.d.cid[src];
+    const int key = p.d.ckey[src];
+    const int s = p.d.cell_start[key], e = p.d.cell_start[key + 1];
+    int dst = a;
+    if (e - s > 8 * p.max_ni + 64) {
+        // far more particles in one cell (edge >= h) than any neighbour list can hold: the search would overflow
+        // MAX_NUM_INTERACTIONS anyway (reference: exit(1)); typical cause is a NaN state collapsing into one cell.
+        // Raise the flag instead of spending O(n^2) here (arrival order is kept).
+        atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
+    } else {
+        int rank = 0;
+        for (int b = s; b < e; ++b) rank += p.d.cid[p.d.perm[b]] < id ? 1 : 0;
+        dst = s + rank;
+    }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         p.d.x[k][dst] = p.d.cx[k][src];
@@ -172,8 +164,8 @@ __global__ void __launch_bounds__(256) k_gather_sorted(const Params p) {
     }
     p.d.m[dst] = p.d.cm[src];
     p.d.u[dst] = p.d.cu[src];
-    p.d.id[dst] = p.d.cid[src];
-    p.d.cell[dst] = p.d.ckey[src];
+    p.d.id[dst] = id;
+    p.d.cell[dst] = key;
 }
 
 } // namespace
@@ -209,9 +201,6 @@ int mlh_launch_sort(mlh_ctx *c) {
     mlh_prof_begin(c, KID_SCATTER);
     k_scatter_perm<<<mlh_blocks(n, 256), 256, 0, st>>>(p);
     mlh_prof_end(c, KID_SCATTER);
-    mlh_prof_begin(c, KID_CELLSORT);
-    k_sort_within_cells<<<mlh_blocks(nc, 128), 128, 0, st>>>(p);
-    mlh_prof_end(c, KID_CELLSORT);
     mlh_prof_begin(c, KID_GATHER);
     if (p.D == 2)
         k_gather_sorted<2><<<mlh_blocks(n, 256), 256, 0, st>>>(p);

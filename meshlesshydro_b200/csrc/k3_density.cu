@@ -12,6 +12,7 @@
 // Roofline: algorithmic bytes 7 (2D) / 11 (3D) doubles per particle; ~35 FP64 ops per neighbour
 // visit (two visits) -> FP64-bound on B200.
 #include "mlh_internal.cuh"
+#include <cfloat>
 
 // LAPACK dgetf2 (partial pivoting) + dtrti2 + unblocked dgetri on an n x n column-major matrix held
 // in registers; same operation order as oracle/mfv_oracle.c:orc_inverse, no FMA contraction.
@@ -103,6 +104,14 @@ template <int D, bool PER>
 __global__ void __launch_bounds__(128) k_density_matrix(const Params p) {
     int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.d.dt_bits = 0x7FEFFFFFFFFFFFFFull; // dt_ = DBL_MAX, Particles.cpp:1447
+    if (!PER && blockIdx.x == 0 && threadIdx.x < 3) {
+        // bounding box of the positions this step will produce (reduced by k_flux_sum_update); same start values as
+        // k_bbox_init (k5_reduce.cu): Particles.cpp:230-231, quirk Q2
+        unsigned long long *keys = (unsigned long long *)p.d.bbox;
+        keys[threadIdx.x] = dbl_key(DBL_MAX);
+        keys[3 + threadIdx.x] = dbl_key(DBL_MIN);
+        p.d.bbox[6 + threadIdx.x] = -DBL_MAX;
+    }
     if (i >= p.own_end) return;
     double xi[3];
 #pragma unroll

@@ -83,18 +83,21 @@ __device__ __forceinline__ double rs_root_pow(const RsConsts &c, double x) {
 struct RsEval {
     double fL, fR, fpL, fpR, wL, wR; // w_K = (Ps/P_K)^((g-1)/2g), rarefaction sides only
 };
-template <bool NEED_FP>
+// RECIP: Ps/P_K is formed as Ps * (1/P_K) with the reciprocals passed in -- k_face_iterate only, where the SAME face may
+// take this path or rs_f_nobranch depending on what the other lanes of its warp are doing: both must round alike, or
+// the result would depend on the (atomic) queue order.
+template <bool NEED_FP, bool RECIP = false>
 __device__ __forceinline__ void rs_eval2(const RsConsts &c, double rhoL, double PL, double aL, double rhoR, double PR,
-                                         double aR, double Ps, RsEval &e) {
+                                         double aR, double Ps, RsEval &e, double iPL = 0., double iPR = 0.) {
     const bool shL = Ps > PL, shR = Ps > PR;
     double wL = 0., wR = 0., rL = 0., rR = 0., qL = 0., qR = 0.;
     if (!shL || !shR) {
         const bool firstL = !shL;
-        const double r1 = Ps / (firstL ? PL : PR);
+        const double r1 = RECIP ? Ps * (firstL ? iPL : iPR) : Ps / (firstL ? PL : PR);
         const double w1 = rs_root_pow(c, r1);
         if (firstL) { wL = w1; rL = r1; } else { wR = w1; rR = r1; }
         if (!shL && !shR) {
-            rR = Ps / PR;
+            rR = RECIP ? Ps * iPR : Ps / PR;
             wR = rs_root_pow(c, rR);
         }
     }
@@ -587,16 +590,14 @@ __device__ __forceinline__ void face_project(const Params &p, int flag, double r
     F[1] = FE;
 }
 
-// device-side dt policy (MeshlessScheme.cpp:91-105): fixed dt, or CFL dt clipped to dt_max
-__global__ void k_select_dt(const Params p, double dt_fixed, double dt_max) {
-    double dt;
-    if (dt_fixed >= 0.) { // 0 is a legal step: the reference driver takes a zero-length step at every dump time (quirk Q7)
-        dt = dt_fixed;
-    } else {
-        dt = __longlong_as_double((long long)*p.d.dt_bits);
-        if (dt_max > 0. && dt > dt_max) dt = dt_max;
-    }
-    *p.d.dt_used = dt;
+// device-side dt policy (MeshlessScheme.cpp:91-105): fixed dt, or CFL dt (min-reduced into dt_bits by K3b, all-reduced
+// over the ranks) clipped to dt_max.  Evaluated by every thread that needs dt (no extra one-thread kernel); the update
+// kernel publishes it in dt_used for the host.
+__device__ __forceinline__ double select_dt(const Params &p, double dt_fixed, double dt_max) {
+    if (dt_fixed >= 0.) return dt_fixed; // 0 is a legal step: the reference driver takes a zero-length step at every dump time (quirk Q7)
+    double dt = __longlong_as_double((long long)*p.d.dt_bits);
+    if (dt_max > 0. && dt > dt_max) dt = dt_max;
+    return dt;
 }
 
 // W component nu -> gradient field slot: W = [rho, P, vx, vy, vz], slots rho 0, vx 1, vy 2, vz 3, P 4
@@ -678,22 +679,112 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
     if (over) atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
 }
 
+#define MLH_PSTAR_VACUUM (-1.) // marker in the P* array: vacuum present or generated, solved in k_face_finish
+template <int D>
+__device__ __forceinline__ void face_load(const double *rec, size_t fs, double *Wa, double *Wb, double *vF, double *A) {
+    using R = FaceRec<D>;
+#pragma unroll
+    for (int nu = 0; nu < D + 2; ++nu) {
+        Wa[nu] = rec[(R::WA + nu) * fs];
+        Wb[nu] = rec[(R::WB + nu) * fs];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        vF[k] = rec[(R::VF + k) * fs];
+        A[k] = rec[(R::AA + k) * fs];
+    }
+}
+
+// queue layout (chunk-sized, SoA): qd[k * cstride + q], k = 0..6 problem (rhoL, PL, aL, rhoR, PR, aR, du), 7..10 start of
+// the root finder (Pguess, f(Pguess), f(0), f'(Pguess)); qi[q] = face index relative to the chunk.  Faces that start
+// with Newton-Raphson are appended from the front (q = 0, 1, ..), faces that start with Brent from the back
+// (q = cstride-1, cstride-2, ..), so that the warps of k_face_iterate work on one kind at a time.  To keep the
+// append counters from serialising (one L2 atomic per warp and kind), the queue is split into MLH_Q_REGIONS regions
+// of equal capacity with their own pair of counters; the warp-tile of 32 faces number t appends to region t % REGIONS.
+#define MLH_Q_FIELDS 11
+#define MLH_Q_REGIONS 128
+__host__ __device__ __forceinline__ int q_region_cap(int cstride) { // faces per region (multiple of 32)
+    const int nwt = (cstride + 31) / 32;
+    return (nwt + MLH_Q_REGIONS - 1) / MLH_Q_REGIONS * 32;
+}
+// Riemann::Riemann + the start of RiemannSolver::solve for one face (body of k_face_setup, also the tail of the fused
+// k_face_states): rotate into the face frame, sound speeds, vacuum test, initial guess, f(0), f(guess).  Faces that
+// need no iteration get P* at once, the others are appended to the solver queue.  The whole warp must call it (ballots);
+// Wa / Wb are rotated in place.
+template <int D>
+__device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid, int fl, double *Wa, double *Wb, const double *A,
+                                                     double *__restrict__ pstar, double *__restrict__ qd, int *__restrict__ qi,
+                                                     int *__restrict__ qcount, int rcap) {
+    const int lane = threadIdx.x & 31;
+    int method = RS_DONE;
+    RsProblem q;
+    RsIter it;
+    if (valid) {
+        FaceFrame<D> fr;
+        face_rotate<D>(A, Wa, Wb, fr);
+        // left = canonical particle a, right = b, along +A (Riemann.cpp:93-94)
+        if (rs_setup(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], q)) {
+            rs_iter_begin(q, it);
+            method = it.method;
+            if (method == RS_DONE) pstar[fl] = it.b;
+        } else {
+            pstar[fl] = MLH_PSTAR_VACUUM;
+        }
+    }
+#pragma unroll
+    for (int kind = RS_NEWTON; kind <= RS_BRENT; ++kind) {
+        const bool mine = method == kind;
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (!m) continue;
+        const int region = (fl >> 5) % MLH_Q_REGIONS;
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(qcount + 2 * region + (kind - RS_NEWTON), __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (mine) {
+            int at = base + __popc(m & ((1u << lane) - 1u));
+            at = region * rcap + (kind == RS_BRENT ? rcap - 1 - at : at);
+            double *d = qd + at;
+            const size_t qs = (size_t)MLH_Q_REGIONS * rcap; // field stride of the queue
+            d[0 * qs] = q.rhoL; d[1 * qs] = q.PL; d[2 * qs] = q.aL; d[3 * qs] = q.rhoR; d[4 * qs] = q.PR; d[5 * qs] = q.aR;
+            d[6 * qs] = q.du;
+            d[7 * qs] = kind == RS_NEWTON ? it.fa : it.a;
+            d[8 * qs] = it.b;
+            d[9 * qs] = kind == RS_NEWTON ? it.fb : it.fa;
+            d[10 * qs] = kind == RS_NEWTON ? it.c : it.fb;
+            qi[at] = fl;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K4a: one thread per (slot, particle)
 // ---------------------------------------------------------------------------------------------
 #ifndef MLH_K4A_BLOCKS_PER_SM
 #define MLH_K4A_BLOCKS_PER_SM 4
 #endif
-template <int D, bool PER>
-__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_states(const Params p, double *__restrict__ stage, int f0, int cstride) {
+#ifndef MLH_FUSE_SETUP
+#define MLH_FUSE_SETUP 0
+#endif
+// FUSE (off): the solver setup (k_face_setup's body) runs on the states while they are still in registers, so the staged
+// record is read once instead of twice.  Measured (A/B, profiles/README.md r01q): no gain at Sedov 61^3 (0.561 ms vs
+// 0.370 + 0.188 ms) and a loss at KH 1M (2.52 vs 0.98 + 1.36 ms) -- 3x the spills and a 75 KB instruction footprint.
+template <int D, bool PER, bool FUSE>
+__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_states(const Params p, double *__restrict__ stage, int f0, int cstride, double dt_fixed, double dt_max,
+                                                                                      double *__restrict__ pstar, double *__restrict__ qd, int *__restrict__ qi, int *__restrict__ qcount) {
     constexpr int NW = D + 2;
     constexpr int PK1 = MLH_PK1(D), PK2 = MLH_PK2(D);
     using R = FaceRec<D>;
     const int nfaces = min(p.d.face_start[p.own_end], p.fcap);
     const int f1 = min(nfaces, f0 + cstride);
-    const double dt = *p.d.dt_used;
+    const double dt = select_dt(p, dt_fixed, dt_max);
     const double gamma = p.gamma;
-    for (int f = f0 + blockIdx.x * MLH_FACE_TILE + threadIdx.x; f < f1; f += gridDim.x * MLH_FACE_TILE) {
+    const int nround = FUSE ? (f1 - f0 + 31) / 32 * 32 : f1 - f0; // FUSE: whole warps stay in the loop (ballots of the queue append)
+    const int rcap = q_region_cap(cstride);
+    for (int fl = blockIdx.x * MLH_FACE_TILE + threadIdx.x; fl < nround; fl += gridDim.x * MLH_FACE_TILE) {
+        const int f = f0 + fl;
+        const bool valid = f < f1;
+        double A[D], Wa[NW], Wb[NW];
+        if (valid) {
         const int fav = p.d.fa[f];
         const int i = fav & 0x7FFFFFFF;
         const int e = p.d.fe[f];
@@ -729,7 +820,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
         }
 
         // ---- effective face A_ab = psi~_b(x_a)/omega_a - psi~_a(x_b)/omega_b (Particles.cpp:1299-1302, :2525-2528) ----
-        double A[D], ga[NW][D], gb[NW][D];
+        double ga[NW][D], gb[NW][D];
         {
             double s1[3], s2[3], d1[D], d2[D];
 #pragma unroll
@@ -768,7 +859,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
         }
 
         // ---- boosted, reconstructed, predicted states (Particles.cpp:1498-1721; ghosts :2546-2672) ----
-        double xjxi[3], xijxi[D], xijxj[D], vF[D], Wa[NW], Wb[NW];
+        double xjxi[3], xijxi[D], xijxj[D], vF[D];
         xjxi[2] = 0.; // quirk Q13 (ZERO_Z): never written in the first-order 3D branch
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -870,6 +961,8 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
             rec[(R::VF + k) * fs] = vF[k];
             rec[(R::AA + k) * fs] = A[k];
         }
+        } // valid
+        if (FUSE) face_setup_and_queue<D>(p, valid, fl, Wa, Wb, A, pstar, qd, qi, qcount, rcap);
     }
 }
 
@@ -892,35 +985,8 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
 #ifndef MLH_K4B_BLOCKS_PER_SM
 #define MLH_K4B_BLOCKS_PER_SM 6
 #endif
-#define MLH_PSTAR_VACUUM (-1.) // marker in the P* array: vacuum present or generated, solved in k_face_finish
 
-template <int D>
-__device__ __forceinline__ void face_load(const double *rec, size_t fs, double *Wa, double *Wb, double *vF, double *A) {
-    using R = FaceRec<D>;
-#pragma unroll
-    for (int nu = 0; nu < D + 2; ++nu) {
-        Wa[nu] = rec[(R::WA + nu) * fs];
-        Wb[nu] = rec[(R::WB + nu) * fs];
-    }
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        vF[k] = rec[(R::VF + k) * fs];
-        A[k] = rec[(R::AA + k) * fs];
-    }
-}
 
-// queue layout (chunk-sized, SoA): qd[k * cstride + q], k = 0..6 problem (rhoL, PL, aL, rhoR, PR, aR, du), 7..10 start of
-// the root finder (Pguess, f(Pguess), f(0), f'(Pguess)); qi[q] = face index relative to the chunk.  Faces that start
-// with Newton-Raphson are appended from the front (q = 0, 1, ..), faces that start with Brent from the back
-// (q = cstride-1, cstride-2, ..), so that the warps of k_face_iterate work on one kind at a time.  To keep the
-// append counters from serialising (one L2 atomic per warp and kind), the queue is split into MLH_Q_REGIONS regions
-// of equal capacity with their own pair of counters; the warp-tile of 32 faces number t appends to region t % REGIONS.
-#define MLH_Q_FIELDS 11
-#define MLH_Q_REGIONS 128
-__host__ __device__ __forceinline__ int q_region_cap(int cstride) { // faces per region (multiple of 32)
-    const int nwt = (cstride + 31) / 32;
-    return (nwt + MLH_Q_REGIONS - 1) / MLH_Q_REGIONS * 32;
-}
 template <int D>
 __global__ void __launch_bounds__(MLH_FACE_TILE) k_face_setup(const Params p, const double *__restrict__ stage, double *__restrict__ pstar,
                                                               double *__restrict__ qd, int *__restrict__ qi, int *__restrict__ qcount,
@@ -929,51 +995,13 @@ __global__ void __launch_bounds__(MLH_FACE_TILE) k_face_setup(const Params p, co
     const int nfaces = min(p.d.face_start[p.own_end], p.fcap);
     const int f1 = min(nfaces, f0 + cstride);
     const size_t fs = (size_t)cstride;
-    const int lane = threadIdx.x & 31;
-    const int nround = (f1 - f0 + 31) / 32 * 32; // whole warps stay in the loop (ballots below)
+    const int nround = (f1 - f0 + 31) / 32 * 32; // whole warps stay in the loop (ballots in face_setup_and_queue)
     const int rcap = q_region_cap(cstride);
     for (int fl = blockIdx.x * MLH_FACE_TILE + threadIdx.x; fl < nround; fl += gridDim.x * MLH_FACE_TILE) {
         const bool valid = f0 + fl < f1;
-        int method = RS_DONE;
-        RsProblem q;
-        RsIter it;
-        if (valid) {
-            double Wa[NW], Wb[NW], vF[D], A[D];
-            FaceFrame<D> fr;
-            face_load<D>(stage + fl, fs, Wa, Wb, vF, A);
-            face_rotate<D>(A, Wa, Wb, fr);
-            // left = canonical particle a, right = b, along +A (Riemann.cpp:93-94)
-            if (rs_setup(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], q)) {
-                rs_iter_begin(q, it);
-                method = it.method;
-                if (method == RS_DONE) pstar[fl] = it.b;
-            } else {
-                pstar[fl] = MLH_PSTAR_VACUUM;
-            }
-        }
-#pragma unroll
-        for (int kind = RS_NEWTON; kind <= RS_BRENT; ++kind) {
-            const bool mine = method == kind;
-            const unsigned m = __ballot_sync(0xffffffffu, mine);
-            if (!m) continue;
-            const int region = (fl >> 5) % MLH_Q_REGIONS;
-            int base = 0;
-            if (lane == __ffs(m) - 1) base = atomicAdd(qcount + 2 * region + (kind - RS_NEWTON), __popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (mine) {
-                int at = base + __popc(m & ((1u << lane) - 1u));
-                at = region * rcap + (kind == RS_BRENT ? rcap - 1 - at : at);
-                double *d = qd + at;
-                const size_t qs = (size_t)MLH_Q_REGIONS * rcap; // field stride of the queue
-                d[0 * qs] = q.rhoL; d[1 * qs] = q.PL; d[2 * qs] = q.aL; d[3 * qs] = q.rhoR; d[4 * qs] = q.PR; d[5 * qs] = q.aR;
-                d[6 * qs] = q.du;
-                d[7 * qs] = kind == RS_NEWTON ? it.fa : it.a;
-                d[8 * qs] = it.b;
-                d[9 * qs] = kind == RS_NEWTON ? it.fb : it.fa;
-                d[10 * qs] = kind == RS_NEWTON ? it.c : it.fb;
-                qi[at] = fl;
-            }
-        }
+        double Wa[NW], Wb[NW], vF[D], A[D];
+        if (valid) face_load<D>(stage + fl, fs, Wa, Wb, vF, A);
+        face_setup_and_queue<D>(p, valid, fl, Wa, Wb, A, pstar, qd, qi, qcount, rcap);
     }
 }
 
@@ -1092,7 +1120,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_i
             if (__any_sync(__activemask(), it.method == RS_NEWTON)) { // Newton starts come first, batch-wise
                 const double trial = rs_iter_trial(it);
                 RsEval e;
-                rs_eval2<true>(p.rs, q.rhoL, q.PL, q.aL, q.rhoR, q.PR, q.aR, trial, e);
+                rs_eval2<true, true>(p.rs, q.rhoL, q.PL, q.aL, q.rhoR, q.PR, q.aR, trial, e, q.iPL, q.iPR);
                 rs_iter_update(it, trial, e.fL + e.fR + q.du, e.fpL + e.fpR);
             } else {
                 rs_brent_step(p.rs, q, it);
@@ -1141,12 +1169,22 @@ __global__ void __launch_bounds__(MLH_FACE_TILE) k_face_finish(const Params p, c
 // K4c / K5: collectFluxes (:1926-2008) in list order + updateStateAndPosition (:2013-2110)
 // ---------------------------------------------------------------------------------------------
 template <int D, bool PER>
-__global__ void __launch_bounds__(128) k_flux_sum_update(const Params p) {
+__global__ void __launch_bounds__(128) k_flux_sum_update(const Params p, double dt_fixed, double dt_max) {
     constexpr int NW = D + 2;
     constexpr int FREC = MLH_FREC(D);
     const int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.own_end) return;
-    const double dt = *p.d.dt_used;
+    // non-periodic runs rebuild the search grid from the particle bounding box every step (MeshlessScheme.cpp:41-51):
+    // the box of the NEW positions is reduced here (getDomainLimits, quirks Q2/Q8; initialised by k_density_matrix), so
+    // the next step starts without a pass over the particles
+    double bmn[D], bmx[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        bmn[k] = DBL_MAX;
+        bmx[k] = DBL_MIN;
+    }
+    const double dt = select_dt(p, dt_fixed, dt_max);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.d.dt_used = dt;
+    if (i < p.own_end) {
     const int ntot = p.d.noi[i] + p.d.noig[i];
     const int fs = p.d.face_start[i];
     double acc[NW];
@@ -1214,14 +1252,29 @@ __global__ void __launch_bounds__(128) k_flux_sum_update(const Params p) {
         }
         p.d.cx[k][o] = x;
         p.d.cv[k][o] = vn[k];
+        xs[k] = x;
     }
     p.d.cm[o] = m;
     p.d.cu[o] = u;
-    p.d.cid[o] = p.d.id[i];
+    const int id = p.d.id[i];
+    p.d.cid[o] = id;
+    if (!PER) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if (xs[k] < bmn[k]) bmn[k] = xs[k];
+            if (id != 0) {
+                if (xs[k] > bmx[k]) bmx[k] = xs[k];
+            } else {
+                p.d.bbox[6 + k] = xs[k];
+            }
+        }
+    }
+    }
+    if (!PER) mlh_bbox_block_reduce<D>(p, bmn, bmx);
 }
 
 template <int D, bool PER>
-int launch_chunks(mlh_ctx *c) {
+int launch_chunks(mlh_ctx *c, double dt_fixed, double dt_max) {
     Params &p = c->p;
     const int n = p.own_end - p.own_begin;
     const int chunk = c->stage_chunk;
@@ -1230,18 +1283,20 @@ int launch_chunks(mlh_ctx *c) {
     // The face count lives on the device (face_start[own_end]); without a host round trip the chunk loop covers the
     // face CAPACITY and the kernels of chunks beyond the last face return at once.  One chunk in the usual case.
     for (long f0 = 0; f0 < p.fcap; f0 += chunk) {
-        mlh_prof_begin(c, KID_FACES);
-        k_face_states<D, PER><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, (int)f0, chunk);
-        mlh_prof_end(c, KID_FACES);
         double *pstar = c->stage + (size_t)FaceRec<D>::NREC * chunk;
         double *qd = pstar + chunk;
         const size_t qs = (size_t)MLH_Q_REGIONS * q_region_cap(chunk);
         int *qi = (int *)(qd + (size_t)MLH_Q_FIELDS * qs);
         int *qcount = qi + qs;
         cudaMemsetAsync(qcount, 0, 2 * MLH_Q_REGIONS * sizeof(int), st);
-        mlh_prof_begin(c, KID_FLUX_SETUP);
-        k_face_setup<D><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, pstar, qd, qi, qcount, (int)f0, chunk);
-        mlh_prof_end(c, KID_FLUX_SETUP);
+        mlh_prof_begin(c, KID_FACES);
+        k_face_states<D, PER, MLH_FUSE_SETUP != 0><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, (int)f0, chunk, dt_fixed, dt_max, pstar, qd, qi, qcount);
+        mlh_prof_end(c, KID_FACES);
+        if (!MLH_FUSE_SETUP) {
+            mlh_prof_begin(c, KID_FLUX_SETUP);
+            k_face_setup<D><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, pstar, qd, qi, qcount, (int)f0, chunk);
+            mlh_prof_end(c, KID_FLUX_SETUP);
+        }
         mlh_prof_begin(c, KID_FLUX);
         k_face_iterate<<<c->num_sms * MLH_K4B_BLOCKS_PER_SM, MLH_FACE_TILE, 0, st>>>(p, pstar, qd, qi, qcount, chunk);
         mlh_prof_end(c, KID_FLUX);
@@ -1250,7 +1305,7 @@ int launch_chunks(mlh_ctx *c) {
         mlh_prof_end(c, KID_FLUX_FINISH);
     }
     mlh_prof_begin(c, KID_UPDATE);
-    k_flux_sum_update<D, PER><<<mlh_blocks(n, 128), 128, 0, st>>>(p);
+    k_flux_sum_update<D, PER><<<mlh_blocks(n > 0 ? n : 1, 128), 128, 0, st>>>(p, dt_fixed, dt_max);
     mlh_prof_end(c, KID_UPDATE);
     return MLH_OK;
 }
@@ -1307,19 +1362,17 @@ int mlh_launch_flux(mlh_ctx *c, double dt_fixed, double dt_max) {
     int n = p.own_end - p.own_begin;
     int rc = mlh_stage_alloc(c);
     if (rc != MLH_OK) return rc;
-    mlh_prof_begin(c, KID_SELECT_DT);
-    k_select_dt<<<1, 1, 0, c->stream>>>(p, dt_fixed, dt_max);
-    mlh_prof_end(c, KID_SELECT_DT);
     if (p.D == 2 && p.periodic)
-        launch_chunks<2, true>(c);
+        launch_chunks<2, true>(c, dt_fixed, dt_max);
     else if (p.D == 2)
-        launch_chunks<2, false>(c);
+        launch_chunks<2, false>(c, dt_fixed, dt_max);
     else if (p.periodic)
-        launch_chunks<3, true>(c);
+        launch_chunks<3, true>(c, dt_fixed, dt_max);
     else
-        launch_chunks<3, false>(c);
+        launch_chunks<3, false>(c, dt_fixed, dt_max);
     MLH_CUDA_CHECK(c, cudaGetLastError());
     p.ncur = n;
+    c->bbox_valid = !p.periodic; // reduced by k_flux_sum_update
     return MLH_OK;
 }
 

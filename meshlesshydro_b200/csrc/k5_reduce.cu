@@ -8,32 +8,13 @@
 
 namespace {
 
-__device__ __forceinline__ void atomic_min_double(double *addr, double v) {
-    // total order trick valid for all finite doubles
-    unsigned long long *a = (unsigned long long *)addr;
-    unsigned long long old = *a, assumed;
-    do {
-        assumed = old;
-        if (!(v < __longlong_as_double((long long)assumed))) break;
-        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
-    } while (assumed != old);
-}
-__device__ __forceinline__ void atomic_max_double(double *addr, double v) {
-    unsigned long long *a = (unsigned long long *)addr;
-    unsigned long long old = *a, assumed;
-    do {
-        assumed = old;
-        if (!(v > __longlong_as_double((long long)assumed))) break;
-        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
-    } while (assumed != old);
-}
-
 __global__ void k_bbox_init(const Params p) {
     int k = threadIdx.x;
     if (k < 3) {
-        p.d.bbox[k] = DBL_MAX;      // running minimum starts at numeric_limits::max()  (:230)
-        p.d.bbox[3 + k] = DBL_MIN;  // running maximum starts at numeric_limits::min()  (:231, quirk Q2)
-        p.d.bbox[6 + k] = -DBL_MAX; // coordinate of original particle 0 (set by whoever owns it)
+        unsigned long long *keys = (unsigned long long *)p.d.bbox;
+        keys[k] = dbl_key(DBL_MAX);     // running minimum starts at numeric_limits::max()  (:230)
+        keys[3 + k] = dbl_key(DBL_MIN); // running maximum starts at numeric_limits::min()  (:231, quirk Q2)
+        p.d.bbox[6 + k] = -DBL_MAX;     // coordinate of original particle 0 (set by whoever owns it)
     }
 }
 
@@ -57,20 +38,7 @@ __global__ void __launch_bounds__(256) k_bbox(const Params p) {
             else p.d.bbox[6 + k] = x;
         }
     }
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double a = __shfl_xor_sync(0xffffffffu, mn[k], o);
-            double b = __shfl_xor_sync(0xffffffffu, mx[k], o);
-            mn[k] = a < mn[k] ? a : mn[k];
-            mx[k] = b > mx[k] ? b : mx[k];
-        }
-        if ((threadIdx.x & 31) == 0) {
-            atomic_min_double(&p.d.bbox[k], mn[k]);
-            atomic_max_double(&p.d.bbox[3 + k], mx[k]);
-        }
-    }
+    mlh_bbox_block_reduce<D>(p, mn, mx);
 }
 
 // Exact Q8 semantics for the one case the parallel reduction cannot see: x[0] is the strict maximum
@@ -84,7 +52,8 @@ template <int D>
 __global__ void k_bbox_replay(const Params p, const int *inv) {
     int k = threadIdx.x;
     if (k >= D) return;
-    if (!(p.d.bbox[6 + k] > p.d.bbox[3 + k])) return;
+    unsigned long long *keys = (unsigned long long *)p.d.bbox;
+    if (!(p.d.bbox[6 + k] > key_dbl(keys[3 + k]))) return;
     double mn = DBL_MAX, mx = DBL_MIN;
     for (int id = 0; id < p.ncur; ++id) {
         double x = p.d.cx[k][inv[id]];
@@ -93,8 +62,8 @@ __global__ void k_bbox_replay(const Params p, const int *inv) {
         else if (x > mx)
             mx = x;
     }
-    p.d.bbox[k] = mn;
-    p.d.bbox[3 + k] = mx;
+    keys[k] = dbl_key(mn);
+    keys[3 + k] = dbl_key(mx);
 }
 
 // sums over the CUR set (state) -- V uses omega of the SRT set (same order)

@@ -470,6 +470,7 @@ int mlh_upload(mlh_ctx *c, long N, const double *x, const double *y, const doubl
     p.own_end = 0;
     c->n_owned = N;
     c->have_state = true;
+    c->bbox_valid = false;
     c->phase = 0;
     return MLH_OK;
 }
@@ -483,11 +484,19 @@ int mlh_build_grid(mlh_ctx *c) {
     Params &p = c->p;
     const bool multi = c->cfg.nranks > 1;
     if (!p.periodic) { // MeshlessScheme.cpp:41-51: grid rebuilt from the particle bounding box every step
-        int rc = mlh_launch_bbox(c);
+        // the update kernel of the previous step has already reduced the box of its new positions (k_flux_sum_update);
+        // a freshly uploaded state needs the stand-alone pass
+        int rc = c->bbox_valid ? MLH_OK : mlh_launch_bbox(c);
         if (rc != MLH_OK) return rc;
+        c->bbox_valid = false;
         if (multi && (rc = mlh_comm_bbox(c)) != MLH_OK) return rc;
         MLH_CUDA_CHECK(c, cudaMemcpyAsync(c->h_small, p.d.bbox, 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         MLH_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < 6; ++k) { // [0..5] travel as order-preserving keys
+            unsigned long long key;
+            memcpy(&key, &c->h_small[k], sizeof(key));
+            c->h_small[k] = key_dbl(key);
+        }
         bool q8 = false; // original particle 0 is the strict maximum along an axis: sequential replay needed
         for (int k = 0; k < p.D; ++k) q8 = q8 || c->h_small[6 + k] > c->h_small[3 + k];
         if (q8) {
@@ -498,6 +507,11 @@ int mlh_build_grid(mlh_ctx *c) {
             if ((rc = mlh_launch_bbox_q8_replay(c)) != MLH_OK) return rc;
             MLH_CUDA_CHECK(c, cudaMemcpyAsync(c->h_small, p.d.bbox, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             MLH_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+            for (int k = 0; k < 6; ++k) {
+                unsigned long long key;
+                memcpy(&key, &c->h_small[k], sizeof(key));
+                c->h_small[k] = key_dbl(key);
+            }
         }
         rc = make_grid(c, c->h_small, c->h_small + 3);
         if (rc != MLH_OK) return rc;

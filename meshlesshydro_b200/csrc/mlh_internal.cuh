@@ -78,7 +78,7 @@ struct DevPtrs {
     double *flux[5]; // mF, eF, vF[3]
     // reductions
     unsigned long long *dt_bits; // min CFL dt as ordered bit pattern
-    double *bbox;                // [0..2] min, [3..5] max over i>=1 (quirk Q8), [6..8] x[0]
+    double *bbox;                // [0..2] min, [3..5] max over i>=1 (quirk Q8) as ORDERED KEYS (dbl_key), [6..8] x[0] as doubles
     double *sums;                // 6 doubles
     unsigned *flags;             // MLH_F_* bits
     unsigned *counters;          // [0] one-sided seam pairs, [3] longest neighbour list of this step (K2)
@@ -104,6 +104,19 @@ struct Params {
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
+
+// Order-preserving 64-bit key of a (non-NaN) double: unsigned comparison of keys == comparison of the doubles, so a
+// bounding box is reduced with native 64-bit atomicMin/atomicMax (and ncclMin/ncclMax on ncclUint64) instead of CAS loops.
+__host__ __device__ __forceinline__ unsigned long long dbl_key(double v) {
+    union { double d; unsigned long long u; } c;
+    c.d = v;
+    return (c.u >> 63) ? ~c.u : (c.u | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double key_dbl(unsigned long long k) {
+    union { double d; unsigned long long u; } c;
+    c.u = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return c.d;
+}
 
 // x*x + y*y (+ z*z) exactly as `pow(dx,2) + pow(dy,2); dSqr += pow(dz,2)` evaluates on the CPU
 // (no FMA contraction): Particles.cpp:342-346.  Bit-exactness of the neighbour sets hangs on this.
@@ -205,6 +218,43 @@ __device__ __forceinline__ void neighbour_geometry(const Params &p, const double
 }
 
 
+// Bounding box of Particles::getDomainLimits (Particles.cpp:228-267): per-thread running min / max (max already
+// excludes original particle 0, quirk Q8; NaN never passes `x < mn` / `x > mx`) -> warp shuffle -> shared memory ->
+// one native atomic per block and bound.  All threads of the block must call it.
+template <int D>
+__device__ __forceinline__ void mlh_bbox_block_reduce(const Params &p, double *mn, double *mx) {
+    __shared__ double red[2 * D][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double a = __shfl_xor_sync(0xffffffffu, mn[k], o);
+            const double b = __shfl_xor_sync(0xffffffffu, mx[k], o);
+            mn[k] = a < mn[k] ? a : mn[k];
+            mx[k] = b > mx[k] ? b : mx[k];
+        }
+        if (lane == 0) {
+            red[k][w] = mn[k];
+            red[D + k][w] = mx[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * D) {
+        const bool is_max = threadIdx.x >= D;
+        double v = red[threadIdx.x][0];
+        for (int q = 1; q < nw; ++q) {
+            const double o = red[threadIdx.x][q];
+            v = is_max ? (o > v ? o : v) : (o < v ? o : v);
+        }
+        unsigned long long *keys = (unsigned long long *)p.d.bbox;
+        if (is_max)
+            atomicMax(keys + 3 + (threadIdx.x - D), dbl_key(v));
+        else
+            atomicMin(keys + threadIdx.x, dbl_key(v));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side context
 // ---------------------------------------------------------------------------------------------
@@ -220,6 +270,7 @@ struct mlh_ctx {
     long n_owned;        // particles owned by this rank
     long capacity;
     bool have_state;     // mlh_upload done
+    bool bbox_valid;     // d.bbox describes the CUR set (reduced by the update kernel of the last step; non-periodic runs)
     int phase;           // 0 = CUR valid (start of step); 1..4 after grid/neighbours/density/gradients
     void *pool;          // single device allocation backing all arrays
     size_t pool_bytes;

@@ -2,5 +2,5 @@
 # A/B timing of alternative builds of the library: MLH_GPU_LIB=<so> quick_bench
 for so in "$@"; do
   echo "=== $so"
-  MLH_GPU_LIB=$PWD/meshlesshydro_b200/$so timeout 300 python tools/quick_bench.py sedov61 kh1000 2>&1 | grep -E "N=|k4|k3b|k2"
+  MLH_GPU_LIB=$PWD/meshlesshydro_b200/$so timeout 300 python tools/quick_bench.py sedov61 kh1000j 2>&1 | grep -E "N=|k0|k1|k4|k3|k2"
 done

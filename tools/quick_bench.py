@@ -5,7 +5,8 @@ import numpy as np
 from meshlesshydro_b200 import capi, ic as IC
 
 def run(name, ic, preset, steps=5, **over):
-    cfg = capi.make_config(preset, ic["h"], ic["gamma"], ic.get("box"), abs_mode=capi.ABS_FABS, **over)
+    over.setdefault("abs_mode", capi.ABS_INT_TRUNC)
+    cfg = capi.make_config(preset, ic["h"], ic["gamma"], ic.get("box"), **over)
     g = capi.MfvGpu(cfg); g.upload(ic)
     N = len(ic["x"])
     for _ in range(2): g.step(want_dt=False)
@@ -28,8 +29,9 @@ for w in which:
     if w == "kh100": run(w, IC.kelvin_helmholtz(100), "kh2d")
     if w == "kh500": run(w, IC.kelvin_helmholtz(500), "kh2d")
     if w == "kh1000": run(w, IC.kelvin_helmholtz(1000), "kh2d")
+    if w == "kh1000j": run(w, IC.kelvin_helmholtz(1000, lattice=True, jitter=0.2), "kh2d", max_interactions=96)
     if w == "kh2000": run(w, IC.kelvin_helmholtz(2000), "kh2d", steps=3)
     if w == "sedov31": run(w, IC.sedov(31), "sedov3d")
-    if w == "sedov61": run(w, IC.sedov(61), "sedov3d")
+    if w == "sedov61": run(w, IC.sedov(61), "sedov3d", abs_mode=capi.ABS_INT_TRUNC, q13_mode=capi.Q13_ZERO_Z, max_interactions=128)
     if w == "sedov128": run(w, IC.sedov(128), "sedov3d", steps=3)
     if w == "fb1000": run(w, IC.fluid_block(1000), "fb2d")
