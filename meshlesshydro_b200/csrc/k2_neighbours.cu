@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
 
     int cnt = 0;
     bool overflow = false;
+    const int idi = p.d.id[i];
     constexpr int NSTENCIL = D == 3 ? 27 : 9;
     // ---- pass A: regular neighbours, Particles.cpp:335-359.  Per stencil cell the thread also records where that
     // cell's group starts in its list (grp) and WHICH particles of the cell it lists (bit k = k-th particle of the
@@ -99,14 +100,27 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
                         e = s;
                     }
                     if (e - s > 64) g0 |= 0x8000u; // more particles than mask bits: the partner searches this group
-                    for (int j = s; j < e; ++j) {
-                        if (j == i) continue;
-                        double d[3];
+                    // four candidates per trip: their loads and cutoff tests are independent (the loop is latency-bound),
+                    // hits are then recorded in ascending j as the reference does
+                    for (int j0 = s; j0 < e; j0 += 4) {
+                        bool hit[4];
 #pragma unroll
-                        for (int k = 0; k < D; ++k) d[k] = __dsub_rn(p.d.x[k][j], xi[k]);
-                        if (dist_sqr_exact<D>(d) < p.hSqr) {
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = j0 + u;
+                            const int jl = j < e ? j : e - 1; // clamped load address for the tail
+                            double d[3];
+#pragma unroll
+                            for (int k = 0; k < D; ++k) d[k] = __dsub_rn(p.d.x[k][jl], xi[k]);
+                            hit[u] = (j < e) && (j != i) && (dist_sqr_exact<D>(d) < p.hSqr);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (!hit[u]) continue;
+                            const int j = j0 + u;
+                            // bits 26..30: stencil cell, bit 31: j has the lower original index -- consumed (and cleared)
+                            // by the ownership pass below, which then needs neither id[j] nor a search for the group
                             if (cnt < p.max_ni)
-                                p.d.nnl[(size_t)cnt * p.ncap + i] = j;
+                                p.d.nnl[(size_t)cnt * p.ncap + i] = j | (sci << MLH_NNL_IDX_BITS) | (p.d.id[j] < idi ? (int)0x80000000 : 0);
                             else
                                 overflow = true;
                             ++cnt;
@@ -187,14 +201,16 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
     // (index of i inside its cell | stencil cell of i as j sees it << 12) for k_face_index. ----
     {
         const int ntot = nreg + ng;
-        const int idi = p.d.id[i];
         const int li = i - p.d.cell_start[c];
-        int nown = 0, cg = 0;
+        const unsigned li_enc = (unsigned)(li < 0xFFF ? li : 0xFFF);
+        int nown = 0;
         for (int s = 0; s < ntot; ++s) {
             const size_t at = (size_t)s * p.ncap + i;
             const int e = p.d.nnl[at];
             const int j = e & MLH_NNL_IDX_MASK;
-            const bool canon = !(p.d.id[j] < idi);
+            const bool regular = !PER || s < nreg;
+            const bool canon = regular ? e >= 0 : !(p.d.id[j] < idi);
+            if (regular) p.d.nnl[at] = j; // strip the tags of pass A
             bool listed = true; // does j list this pair too?  (the test of pass B from j's side; exact for regular pairs)
             if (PER && s >= nreg && !p.symmetric_seam) {
                 const int cview = reverse_code((int)((unsigned)e >> MLH_NNL_IDX_BITS)); // image of i as j sees it
@@ -213,10 +229,9 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
             if (own) {
                 v = ((unsigned)nown << 2) | 2u | (canon ? 0u : 1u);
                 ++nown;
-            } else if (s < nreg) {
-                // stencil cell of this slot: the last group that starts at or before s
-                while (cg + 1 < NSTENCIL && (int)(p.d.grp[(size_t)(cg + 1) * p.ncap + i] & 0x7FFFu) <= s) ++cg;
-                v = ((unsigned)((li < 0xFFF ? li : 0xFFF) | ((NSTENCIL - 1 - cg) << 12))) << 2;
+            } else if (regular) {
+                const int cg = (e >> MLH_NNL_IDX_BITS) & 31; // stencil cell of this slot (tag of pass A)
+                v = (li_enc | ((unsigned)(NSTENCIL - 1 - cg) << 12)) << 2;
             } else {
                 v = MLH_FMAP_GHOST_SEARCH;
             }

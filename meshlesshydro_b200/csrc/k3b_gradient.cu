@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(128, 4) k_gradient_limit(const Params p) {
         // quirk Q7; it needs the same |x_i - x_j| as the kernel weight, so it rides along here) ----
         double vSig = DBL_MIN; // quirk Q2
         const double ci = own[2 * D + 2];
-        int e_next = ntot > 0 ? p.d.nnl[i] : 0; // list entries are fetched one visit ahead of the record gather
+        // list entries are fetched one visit ahead of the record gather (an L1 prefetch of the next record on top of
+        // that cost more LSU issue than it hid: 0.199 -> 0.216 ms at 61^3, profiles/README.md r01t)
+        int e_next = ntot > 0 ? p.d.nnl[i] : 0;
         for (int s = 0; s < ntot; ++s) {
             const int e = e_next;
             if (s + 1 < ntot) e_next = p.d.nnl[(size_t)(s + 1) * p.ncap + i];

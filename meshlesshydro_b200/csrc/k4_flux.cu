@@ -37,6 +37,7 @@
 // written once and read once).
 #include "mlh_internal.cuh"
 #include <cfloat>
+#include <cstdlib>
 #include <cuda_pipeline.h>
 
 namespace {
@@ -467,16 +468,13 @@ __device__ __forceinline__ PairLimits pairwise_limits(const Params &p, double ph
 }
 // ratio = |x_ij - x_i| / |x_j - x_i| (evaluated once per side: `xijxi_abs / xjxi_abs * (phi_j - phi_i)` is left-associative)
 __device__ __forceinline__ double pairwise_limiter(const PairLimits &l, double phi0, double phi_i, double phi_j, double ratio) {
-    double phi_ = phi_i;
+    // the two branches of the reference (phi_i < phi_j / phi_i > phi_j) as selects: in a warp both occur, lane by lane
+    const bool lt = phi_i < phi_j, gt = phi_i > phi_j;
     const double phi_ij = phi_i + ratio * (phi_j - phi_i);
-    if (phi_i < phi_j) {
-        const double minPhiD2 = (phi_ij + l.delta2 < phi0) ? phi_ij + l.delta2 : phi0;
-        phi_ = l.phiMinus > minPhiD2 ? l.phiMinus : minPhiD2;
-    } else if (phi_i > phi_j) {
-        const double maxPhiD2 = (phi_ij - l.delta2 > phi0) ? phi_ij - l.delta2 : phi0;
-        phi_ = l.phiPlus < maxPhiD2 ? l.phiPlus : maxPhiD2;
-    }
-    return phi_;
+    const double t = lt ? phi_ij + l.delta2 : phi_ij - l.delta2;
+    const double m = lt ? ((t < phi0) ? t : phi0) : ((t > phi0) ? t : phi0);         // minPhiD2 / maxPhiD2
+    const double r = lt ? (l.phiMinus > m ? l.phiMinus : m) : (l.phiPlus < m ? l.phiPlus : m);
+    return (lt || gt) ? r : phi_i;
 }
 
 template <int D>
@@ -780,14 +778,29 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
     const double gamma = p.gamma;
     const int nround = FUSE ? (f1 - f0 + 31) / 32 * 32 : f1 - f0; // FUSE: whole warps stay in the loop (ballots of the queue append)
     const int rcap = q_region_cap(cstride);
-    for (int fl = blockIdx.x * MLH_FACE_TILE + threadIdx.x; fl < nround; fl += gridDim.x * MLH_FACE_TILE) {
+    // The face list is read one trip ahead, and the gather records of the NEXT trip's endpoints are prefetched into L1
+    // while this trip computes: a block's 128 consecutive faces belong to ~8 neighbouring owners that share most of
+    // their partners, ~50 distinct records (11 KB) per trip -- the kernel was waiting on exactly those first-touch
+    // misses (long-scoreboard 5.9 of 10 stalled warps at 25 % occupancy, profiles/r01s).
+    const int stride = gridDim.x * MLH_FACE_TILE;
+    int fl = blockIdx.x * MLH_FACE_TILE + threadIdx.x;
+    int fav_next = 0, e_next = 0;
+    if (fl < nround && f0 + fl < f1) {
+        fav_next = p.d.fa[f0 + fl];
+        e_next = p.d.fe[f0 + fl];
+    }
+    for (; fl < nround; fl += stride) {
         const int f = f0 + fl;
         const bool valid = f < f1;
+        const int fav = fav_next, e = e_next;
+        const bool valid_next = fl + stride < nround && f + stride < f1;
+        if (valid_next) {
+            fav_next = p.d.fa[f + stride];
+            e_next = p.d.fe[f + stride];
+        }
         double A[D], Wa[NW], Wb[NW];
         if (valid) {
-        const int fav = p.d.fa[f];
         const int i = fav & 0x7FFFFFFF;
-        const int e = p.d.fe[f];
         const int j = e & MLH_NNL_IDX_MASK;
         const int code = PER ? (int)((unsigned)e >> MLH_NNL_IDX_BITS) : 0;
         // canonical orientation: the endpoint with the lower ORIGINAL index plays "i" (Particles.cpp:1841,1889);
@@ -856,6 +869,26 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_s
                     ga[nu][k] = A2[D * D + nu * D + k];
                     gb[nu][k] = B2[D * D + nu * D + k];
                 }
+        }
+
+        if (valid_next) { // the list entries of the next trip have arrived by now; start its record fetches
+            const int in = fav_next & 0x7FFFFFFF, jn = e_next & MLH_NNL_IDX_MASK;
+            const char *r1i = (const char *)(p.d.pk1 + (size_t)in * PK1), *r1j = (const char *)(p.d.pk1 + (size_t)jn * PK1);
+            const char *r2i = (const char *)(p.d.pk2 + (size_t)in * PK2), *r2j = (const char *)(p.d.pk2 + (size_t)jn * PK2);
+#pragma unroll
+            for (int o = 0; o < PK1 * 8; o += 128) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r1i + o));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r1j + o));
+            }
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(r1i + PK1 * 8 - 8));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(r1j + PK1 * 8 - 8));
+#pragma unroll
+            for (int o = 0; o < PK2 * 8; o += 128) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r2i + o));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r2j + o));
+            }
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(r2i + PK2 * 8 - 8));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(r2j + PK2 * 8 - 8));
         }
 
         // ---- boosted, reconstructed, predicted states (Particles.cpp:1498-1721; ghosts :2546-2672) ----
@@ -1279,6 +1312,12 @@ int launch_chunks(mlh_ctx *c, double dt_fixed, double dt_max) {
     const int n = p.own_end - p.own_begin;
     const int chunk = c->stage_chunk;
     const int grid_persistent = c->num_sms * 8;
+    // blocks per SM of the streaming face kernels (setup / finish): tunable for A/B runs
+    // (tools/grid_sweep.sh, profiles/README.md r01t: setup 8 -> 16 blocks/SM 0.193 -> 0.157 ms at 61^3 and 1.36 -> 1.31 ms
+    // at KH 1M; finish holds 6 blocks/SM by registers: one clean wave is best in 3D (0.157 -> 0.125 ms), 8 in 2D)
+    static const int g_setup = getenv("MLH_GRID_SETUP") ? atoi(getenv("MLH_GRID_SETUP")) : 16;
+    static const int g_finish = getenv("MLH_GRID_FINISH") ? atoi(getenv("MLH_GRID_FINISH")) : (D == 3 ? 6 : 8);
+    static const int g_states = getenv("MLH_GRID_STATES") ? atoi(getenv("MLH_GRID_STATES")) : 8;
     cudaStream_t st = c->stream;
     // The face count lives on the device (face_start[own_end]); without a host round trip the chunk loop covers the
     // face CAPACITY and the kernels of chunks beyond the last face return at once.  One chunk in the usual case.
@@ -1290,18 +1329,18 @@ int launch_chunks(mlh_ctx *c, double dt_fixed, double dt_max) {
         int *qcount = qi + qs;
         cudaMemsetAsync(qcount, 0, 2 * MLH_Q_REGIONS * sizeof(int), st);
         mlh_prof_begin(c, KID_FACES);
-        k_face_states<D, PER, MLH_FUSE_SETUP != 0><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, (int)f0, chunk, dt_fixed, dt_max, pstar, qd, qi, qcount);
+        k_face_states<D, PER, MLH_FUSE_SETUP != 0><<<c->num_sms * g_states, MLH_FACE_TILE, 0, st>>>(p, c->stage, (int)f0, chunk, dt_fixed, dt_max, pstar, qd, qi, qcount);
         mlh_prof_end(c, KID_FACES);
         if (!MLH_FUSE_SETUP) {
             mlh_prof_begin(c, KID_FLUX_SETUP);
-            k_face_setup<D><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, pstar, qd, qi, qcount, (int)f0, chunk);
+            k_face_setup<D><<<c->num_sms * g_setup, MLH_FACE_TILE, 0, st>>>(p, c->stage, pstar, qd, qi, qcount, (int)f0, chunk);
             mlh_prof_end(c, KID_FLUX_SETUP);
         }
         mlh_prof_begin(c, KID_FLUX);
         k_face_iterate<<<c->num_sms * MLH_K4B_BLOCKS_PER_SM, MLH_FACE_TILE, 0, st>>>(p, pstar, qd, qi, qcount, chunk);
         mlh_prof_end(c, KID_FLUX);
         mlh_prof_begin(c, KID_FLUX_FINISH);
-        k_face_finish<D><<<grid_persistent, MLH_FACE_TILE, 0, st>>>(p, c->stage, pstar, (int)f0, chunk);
+        k_face_finish<D><<<c->num_sms * g_finish, MLH_FACE_TILE, 0, st>>>(p, c->stage, pstar, (int)f0, chunk);
         mlh_prof_end(c, KID_FLUX_FINISH);
     }
     mlh_prof_begin(c, KID_UPDATE);
