@@ -337,19 +337,26 @@ def main():
         out = {k: (capi.pinned_empty(n_out) if k in names else None) for k in ["x", "y", "z", "vx", "vy", "vz", "m", "u"]}
         out["ids"] = capi.pinned_empty(n_out, np.int32)
         esteps = max(3, min(args.steps, 10))
+        out_ic = dict(ic_local)
+        out_ic.update({k: out[k] for k in names})
         for _ in range(2):
             gpu.upload(host_ic, ids=ids_local)
             gpu.step(want_dt=False)
             gpu.download_state(out)
         barrier()
         t0 = time.perf_counter()
+        src, dst = host_ic, out
         for _ in range(esteps):
-            gpu.upload(host_ic, ids=ids_local)  # H2D of this step's inputs
+            gpu.upload(src, ids=ids_local)      # H2D of this step's inputs
             gpu.step(want_dt=False)
-            gpu.download_state(out)             # D2H of the step's result (synchronises)
+            gpu.download_state(dst)             # D2H of the step's result (synchronises)
             if world == 1:
-                for k in names:                 # next step starts from the downloaded state (host round trip)
-                    host[k][:] = out[k]
+                # the next step starts from the state just downloaded (host round trip): the two sets of pinned
+                # buffers swap roles, as a host code that owns its particle arrays would do
+                if src is host_ic:
+                    src, dst = out_ic, {**{k: (host[k] if k in names else None) for k in out if k != "ids"}, "ids": out["ids"]}
+                else:
+                    src, dst = host_ic, out
         barrier()
         e_s = max_over_ranks(time.perf_counter() - t0)
         nb = len(names) * 8 * n_local

@@ -744,9 +744,13 @@ int mlh_download_diag(mlh_ctx *c, double *rho, double *P, double *rhoGrad, int *
     one(p.d.rho + o, rho);
     one(p.d.P + o, P);
     if (rhoGrad && rc == MLH_OK) {
-        if (c->cfg.nranks > 1) {
-            snprintf(c->err, sizeof(c->err), "mlh_download_diag: rhoGrad with nranks>1 -> use mlh_debug_fetch per component");
-            rc = MLH_E_INVALID;
+        if (c->cfg.nranks > 1) { // device order like the state (ids from mlh_download_state), interleaved on the host
+            std::vector<double> comp((size_t)n);
+            for (int a = 0; a < D; ++a) {
+                cudaMemcpyAsync(comp.data(), p.d.g[0 * 3 + a] + o, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+                cudaStreamSynchronize(c->stream);
+                for (int i = 0; i < n; ++i) rhoGrad[(size_t)i * D + a] = comp[(size_t)i];
+            }
         } else {
             for (int a = 0; a < D && rc == MLH_OK; ++a) rc = mlh_launch_unpermute_f64(c, p.d.g[0 * 3 + a] + o, ids, tmp, n, a, D);
             cudaMemcpyAsync(rhoGrad, tmp, sizeof(double) * (size_t)n * D, cudaMemcpyDeviceToHost, c->stream);

@@ -21,6 +21,7 @@
 #define DEMONSTRATOR_PARTICLES_H
 
 #include <string>
+#include <vector>
 
 #include "parameter.h"
 #include "Domain.h"
@@ -96,6 +97,7 @@ public:
 private:
     enum Phase { PH_STATE = 0, PH_GRID = 1, PH_NEIGHBOURS = 2, PH_DENSITY = 3, PH_GRADIENTS = 4 };
     void ensure(int phase); // run the device phases up to `phase`
+    void selectShard();     // multi-rank runs: original indices of the particles in this rank's slab
     void check(int rc, const char *what);
     void checkFlags();
     void sums();
@@ -109,6 +111,7 @@ private:
     double hCfg{0.}, gammaCfg{0.};
     double boxCfg[2 * DIM];
     bool configured{false};
+    std::vector<int> shardIds;
 };
 
 #endif // DEMONSTRATOR_PARTICLES_H

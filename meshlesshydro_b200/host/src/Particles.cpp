@@ -3,6 +3,7 @@
 #include "../include/Particles.h"
 
 #include <cfloat>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -10,10 +11,13 @@
 
 #include "../../../include/mlh_gpu.h"
 #include "../include/H5Lite.h"
+#include "../include/MultiGpu.h"
 
 namespace {
 bool g_pinned_ok = true;
 template <typename T> T *hostArray(size_t n) {
+    // multi-rank runs (MultiGpu.h): the public arrays are ONE copy shared by all rank processes
+    if (mgpu::planned() > 1) return (T *)mgpu::sharedAlloc((n ? n : 1) * sizeof(T));
     if (g_pinned_ok) {
         void *p = nullptr;
         if (mlh_host_alloc((n ? n : 1) * sizeof(T), &p) == MLH_OK) {
@@ -27,13 +31,17 @@ template <typename T> T *hostArray(size_t n) {
     return p;
 }
 template <typename T> void hostFree(T *p) {
-    if (!p) return;
+    if (!p || mgpu::planned() > 1) return; // shared mappings go with the process
     if (g_pinned_ok) mlh_host_free((void *)p);
     else std::free((void *)p);
 }
 int envInt(const char *name, int dflt) {
     const char *v = std::getenv(name);
     return v && *v ? std::atoi(v) : dflt;
+}
+[[noreturn]] void die(int code) {
+    if (mgpu::active()) mgpu::fail(); // the other ranks may be blocked in a barrier or an NCCL call
+    exit(code);
 }
 } // namespace
 
@@ -80,7 +88,7 @@ Particles::~Particles() {
 void Particles::check(int rc, const char *what) {
     if (rc == MLH_OK) return;
     Logger(ERROR) << what << " failed (" << rc << "): " << mlh_last_error(gpu) << " - Aborting.";
-    exit(rc == MLH_E_NO_DEVICE ? 20 : 21);
+    die(rc == MLH_E_NO_DEVICE ? 20 : 21);
 }
 
 // device error flags -> the reference's messages and exit codes
@@ -89,16 +97,16 @@ void Particles::checkFlags() {
     if (f & MLH_F_MAX_INTERACTIONS) {
         Logger(ERROR) << "MAX_NUM_INTERACTIONS exceeded for at least one particle (device list capacity "
                       << envInt("MLH_MAX_INTERACTIONS", 0) << ", 0 = default) - Aborting."; // Particles.cpp:348-352 / :2249-2253
-        exit(1);
+        die(1);
     }
     if (f & MLH_F_OUT_OF_GRID) {
         Logger(ERROR) << "Particle outside of the search grid. - Aborting.";
-        exit(2);
+        die(2);
     }
 #if DEBUG_LVL
     if (f & MLH_F_NEG_GHOST_PRESSURE) {
         Logger(ERROR) << "Negative pressure encountered @ghost face. Very bad :( !!"; // Particles.cpp:1873-1881
-        exit(6);
+        die(6);
     }
 #endif
     if (f & MLH_F_VACUUM) Logger(WARN) << "  > Vacuum state sampled. This is not expected."; // Riemann.cpp:113,126
@@ -112,12 +120,48 @@ void Particles::configureDevice(const double &kernelSize, const double &gamma, c
     configured = true;
 }
 
+// The particles this rank owns: whole cell layers of the search grid along the slowest-varying axis (y in 2D, z in 3D:
+// cell id = iX + iY cellsX + iZ cellsX cellsY, Particles.cpp:298-302), the same split the device uses (mlh_slab_range).
+// Grid as Domain::createGrid builds it (Domain.cpp:9-54) from the periodic box or from getDomainLimits.
+void Particles::selectShard() {
+    double lim[2 * DIM];
+#if PERIODIC_BOUNDARIES
+    for (int k = 0; k < 2 * DIM; ++k) lim[k] = boxCfg[k];
+#else
+    getDomainLimits(lim); // host loop: nothing is on the device yet
+#endif
+    const int k = DIM - 1;
+    const double *coord = y;
+#if DIM == 3
+    coord = z;
+#endif
+    const double lo = lim[k], hi = lim[DIM + k];
+    const int layers = (int)std::floor((hi - lo) / hCfg);
+    if (layers < 2 * mgpu::nranks()) {
+        Logger(ERROR) << "slab decomposition needs >= 2 cell layers per rank (" << layers << " layers, " << mgpu::nranks()
+                      << " ranks) - Aborting.";
+        die(21);
+    }
+    const double size = (hi - lo) / layers;
+    int first = 0, last = 0;
+    if (mlh_slab_range(layers, mgpu::nranks(), mgpu::rank(), &first, &last) != MLH_OK) {
+        Logger(ERROR) << "mlh_slab_range failed - Aborting.";
+        die(21);
+    }
+    shardIds.clear();
+    for (int i = 0; i < N; ++i) {
+        int layer = (int)std::floor((coord[i] - lo) / size);
+        if (layer == layers) layer -= 1; // Particles.cpp:283-295
+        if (layer >= first && layer < last) shardIds.push_back(i);
+    }
+}
+
 void Particles::ensure(int target) {
     if (ghostHolder) return;
     if (!gpu) {
         if (!configured) {
             Logger(ERROR) << "Particles: configureDevice(kernelSize, gamma, box) must precede the first phase. - Aborting.";
-            exit(21);
+            die(21);
         }
         mlh_config cfg;
         mlh_default_config(&cfg);
@@ -143,11 +187,49 @@ void Particles::ensure(int target) {
         cfg.gamma = gammaCfg;
         for (int k = 0; k < 2 * DIM; ++k) cfg.box[k] = boxCfg[k];
         cfg.device = envInt("MLH_DEVICE", 0);
+        if (mgpu::active()) { // one rank per GPU, slab decomposition (MultiGpu.h)
+            cfg.rank = mgpu::rank();
+            cfg.nranks = mgpu::nranks();
+            cfg.device = envInt("MLH_DEVICE", 0) + mgpu::rank();
+            selectShard();
+            const long share = (long)((double)N / mgpu::nranks() * 1.6) + 8192, mine = (long)((double)shardIds.size() * 1.6) + 8192;
+            cfg.capacity = share > mine ? share : mine;
+        }
         int rc = mlh_create(&cfg, &gpu);
         if (rc != MLH_OK) {
             Logger(ERROR) << "mlh_create failed (" << rc << "): " << mlh_last_error(nullptr) << " - Aborting.";
-            exit(rc == MLH_E_NO_DEVICE ? 20 : 21);
+            die(rc == MLH_E_NO_DEVICE ? 20 : 21);
         }
+        if (mgpu::active()) {
+            if (mgpu::rank() == 0) check(mlh_comm_unique_id(mgpu::ncclId()), "mlh_comm_unique_id");
+            mgpu::barrier();
+            check(mlh_comm_init(gpu, mgpu::ncclId()), "mlh_comm_init");
+        }
+    }
+    if (hostDirty && mgpu::active()) {
+        // upload the particles of this rank's slab with their original indices
+        if (shardIds.empty() && N > 0) selectShard();
+        const size_t n = shardIds.size();
+        std::vector<double> buf[8];
+        const double *src[8] = {x, y, nullptr, vx, vy, nullptr, m, u};
+#if DIM == 3
+        src[2] = z;
+        src[5] = vz;
+#endif
+        for (int f = 0; f < 8; ++f) {
+            if (!src[f]) continue;
+            buf[f].resize(n);
+            for (size_t k = 0; k < n; ++k) buf[f][k] = src[f][shardIds[k]];
+        }
+        check(mlh_upload(gpu, (long)n, buf[0].data(), buf[1].data(), src[2] ? buf[2].data() : nullptr, buf[3].data(), buf[4].data(),
+                         src[5] ? buf[5].data() : nullptr, buf[6].data(), buf[7].data(), shardIds.data()),
+              "mlh_upload");
+        shardIds.clear(); // ownership moves with the particles from now on
+        shardIds.shrink_to_fit();
+        hostDirty = false;
+        hostStale = false;
+        phase = PH_STATE;
+        sumsValid = false;
     }
     if (hostDirty) {
         const double *zz = nullptr, *vzz = nullptr;
@@ -229,7 +311,7 @@ void Particles::gradient(double *f, double (*grad)[DIM]) {
         ;
     if (!known) {
         Logger(ERROR) << "Particles::gradient: only the gradients of rho, vx, vy, vz, P are computed on the device. - Aborting.";
-        exit(21);
+        die(21);
     }
     ensure(PH_GRADIENTS);
 }
@@ -319,6 +401,39 @@ double Particles::sumMomentumZ() { sums(); return sumCache[5]; }
 
 void Particles::syncHost() {
     if (ghostHolder || !gpu || hostDirty) return;
+    if (mgpu::active()) {
+        // every rank scatters its owned particles (device order + original ids) into the shared host arrays
+        const long n = mlh_num_particles(gpu);
+        std::vector<double> b[8];
+        for (auto &v : b) v.resize((size_t)(n > 0 ? n : 1));
+        std::vector<int> ids((size_t)(n > 0 ? n : 1));
+        const bool three = DIM == 3;
+        check(mlh_download_state(gpu, b[0].data(), b[1].data(), three ? b[2].data() : nullptr, b[3].data(), b[4].data(),
+                                 three ? b[5].data() : nullptr, b[6].data(), b[7].data(), ids.data()),
+              "mlh_download_state");
+        for (long q = 0; q < n; ++q) {
+            const int i = ids[(size_t)q];
+            x[i] = b[0][q]; y[i] = b[1][q]; vx[i] = b[3][q]; vy[i] = b[4][q]; m[i] = b[6][q]; u[i] = b[7][q];
+#if DIM == 3
+            z[i] = b[2][q]; vz[i] = b[5][q];
+#endif
+        }
+        if (phase >= PH_GRADIENTS) {
+            std::vector<double> g((size_t)(n > 0 ? n : 1) * DIM);
+            std::vector<int> cnt((size_t)(n > 0 ? n : 1));
+            check(mlh_download_diag(gpu, b[0].data(), b[1].data(), g.data(), cnt.data()), "mlh_download_diag");
+            for (long q = 0; q < n; ++q) {
+                const int i = ids[(size_t)q];
+                rho[i] = b[0][q];
+                P[i] = b[1][q];
+                noi[i] = cnt[(size_t)q];
+                for (int a = 0; a < DIM; ++a) rhoGrad[i][a] = g[(size_t)q * DIM + a];
+            }
+        }
+        mgpu::barrier(); // all slabs are in
+        hostStale = false;
+        return;
+    }
     double *zz = nullptr, *vzz = nullptr;
 #if DIM == 3
     zz = z;
@@ -347,6 +462,13 @@ void Particles::dump2file(std::string filename, double simTime) {
     ensure(PH_GRADIENTS);
     syncHost();
     const double t = simTime, mass = sumMass(), energy = sumEnergy(), px = sumMomentumX(), py = sumMomentumY();
+#if DIM == 3
+    const double pz = sumMomentumZ();
+#endif
+    if (mgpu::active() && mgpu::rank() != 0) { // the sums above are collective; the file is rank 0's job
+        mgpu::barrier();
+        return;
+    }
     std::vector<double> pos((size_t)N * DIM), vel((size_t)N * DIM);
     for (int i = 0; i < N; ++i) {
         pos[(size_t)i * DIM] = x[i];
@@ -367,7 +489,6 @@ void Particles::dump2file(std::string filename, double simTime) {
         w.write("/xMomentum", one, &px);
         w.write("/yMomentum", one, &py);
 #if DIM == 3
-        const double pz = sumMomentumZ();
         w.write("/zMomentum", one, &pz);
 #endif
         w.write("/rho", n1, rho);
@@ -381,6 +502,8 @@ void Particles::dump2file(std::string filename, double simTime) {
         w.close();
     } catch (const std::exception &e) {
         Logger(ERROR) << "dump2file(" << filename << "): " << e.what();
+        if (mgpu::active()) die(21);
         throw;
     }
+    mgpu::barrier(); // the other ranks wait until the shared arrays have been written out
 }

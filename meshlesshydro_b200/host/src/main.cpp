@@ -2,6 +2,7 @@
 // (-c/--config, -v/--verbose, -s/--silent, -h/--help; initFile, outDir, timeStep, timeEnd, h5DumpInterval,
 // kernelSize, gamma, periodicBoxLimits{lowerX..upperZ}).  No cxxopts / Boost.
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <stdexcept>
@@ -9,6 +10,7 @@
 #include "../include/ConfigParser.h"
 #include "../include/Logger.h"
 #include "../include/MeshlessScheme.h"
+#include "../include/MultiGpu.h"
 
 structlog LOGCFG = {};
 
@@ -18,12 +20,14 @@ static void usage() {
                  "  -c, --config arg  Path to config file (default: config.info)\n"
                  "  -v, --verbose     More printouts for debugging\n"
                  "  -s, --silent      Suppress normal printouts\n"
+                 "  -n, --ranks arg   GPUs of this node to use, one process each (default: $MLH_RANKS or 1)\n"
                  "  -h, --help        Show this help\n";
 }
 
 int main(int argc, char *argv[]) {
     std::string configFile = "config.info";
     bool verbose = false, silent = false;
+    int ranks = std::getenv("MLH_RANKS") ? std::atoi(std::getenv("MLH_RANKS")) : 1;
     for (int a = 1; a < argc; ++a) {
         const std::string arg = argv[a];
         if (arg == "-h" || arg == "--help") {
@@ -37,6 +41,10 @@ int main(int argc, char *argv[]) {
             configFile = argv[++a];
         } else if (arg.rfind("--config=", 0) == 0) {
             configFile = arg.substr(9);
+        } else if ((arg == "-n" || arg == "--ranks") && a + 1 < argc) {
+            ranks = std::atoi(argv[++a]);
+        } else if (arg.rfind("--ranks=", 0) == 0) {
+            ranks = std::atoi(arg.substr(8).c_str());
         } else {
             std::cerr << "Option '" << arg << "' does not exist" << std::endl;
             return 1;
@@ -86,11 +94,17 @@ int main(int argc, char *argv[]) {
     Logger(INFO) << "    > Periodic boundaries within box: " << periodicBoxStr << "]";
 #endif
 
+    mgpu::plan(ranks); // before the particle arrays exist: with several ranks they live in shared memory
     Logger(INFO) << "    > Reading initial distribution ...";
     InitialDistribution initDist{config.initFile};
     Particles particles{initDist.getNumberOfParticles()};
     initDist.getAllParticles(particles);
     Logger(INFO) << "    > N = " << particles.N;
+    if (mgpu::planned() > 1) {
+        Logger(INFO) << "    > Slab decomposition over " << mgpu::planned() << " GPUs (one process each)";
+        mgpu::launch(); // no CUDA call so far; the parent continues as rank 0
+        if (mgpu::rank() != 0) LOGCFG.level = ERROR;
+    }
     Logger(INFO) << "... done. Initializing simulation ...";
 
 #if PERIODIC_BOUNDARIES
@@ -109,6 +123,6 @@ int main(int argc, char *argv[]) {
     if (algorithm.stepsDone() > 0)
         Logger(INFO) << "    > " << algorithm.stepsDone() << " steps, " << algorithm.secondsInLoop() << " s in the time loop ("
                      << (double)particles.N * algorithm.stepsDone() / algorithm.secondsInLoop() << " particle-updates/s, "
-                     << particles.kernelLaunches() << " kernel launches)";
-    return 0;
+                     << particles.kernelLaunches() << " kernel launches" << (mgpu::active() ? " on rank 0)" : ")");
+    return mgpu::finish(0);
 }

@@ -171,3 +171,32 @@ def test_helper_domain_particles_host_parts(case, dim):
     lim = [float(v) for v in r["limits"].split()]
     assert lim[0] == -0.3 and lim[dim] == 0.7               # Particles::getDomainLimits
     assert r["logger"] == "42"                              # INFO line printed, DEBUG line filtered
+
+
+def test_multi_rank_launcher_fails_loudly_without_gpus(tmp_path):
+    """`mlh_kh2d --ranks 2` on a box without GPUs: both rank processes must end with the no-device error (exit 20) --
+    no CPU fallback, and no rank left hanging in a barrier (host/src/MultiGpu.cpp)."""
+    import subprocess
+    import numpy as np
+    from meshlesshydro_b200 import h5lite, ic as IC
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    exe = os.path.join(HOST, "bin", "mlh_kh2d")
+    if not os.path.exists(exe):
+        pytest.skip("host executables not built")
+    ic = IC.kelvin_helmholtz(16, lattice=False)
+    init = str(tmp_path / "init.h5")
+    h5lite.write_initial_conditions(init, ic)
+    (tmp_path / "out").mkdir()
+    cfg = tmp_path / "config.info"
+    cfg.write_text("initFile %s\noutDir %s\ntimeStep 0.01\ntimeEnd 0.02\nh5DumpInterval 1\nperiodicBoxLimits {\n lowerX 0\n lowerY 0\n"
+                   " upperX 1\n upperY 1\n}\nkernelSize %.17g\ngamma %.17g\n" % (init, tmp_path / "out", ic["h"], ic["gamma"]))
+    r = subprocess.run([exe, "-c", str(cfg), "--ranks", "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+    assert r.returncode != 0, r.stdout[-2000:]
+    assert "Slab decomposition over 2 GPUs" in r.stdout
+    assert "mlh_create failed" in r.stdout
+    assert os.listdir(tmp_path / "out") == []
