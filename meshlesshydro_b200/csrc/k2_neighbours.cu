@@ -204,9 +204,16 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
         const int li = i - p.d.cell_start[c];
         const unsigned li_enc = (unsigned)(li < 0xFFF ? li : 0xFFF);
         int nown = 0;
-        for (int s = 0; s < ntot; ++s) {
+        for (int s0 = 0; s0 < ntot; s0 += 4) {
+          int e4[4]; // the entries of four slots are read back together (independent loads)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) e4[q] = p.d.nnl[(size_t)(s0 + q < ntot ? s0 + q : ntot - 1) * p.ncap + i];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int s = s0 + q;
+            if (s >= ntot) break;
             const size_t at = (size_t)s * p.ncap + i;
-            const int e = p.d.nnl[at];
+            const int e = e4[q];
             const int j = e & MLH_NNL_IDX_MASK;
             const bool regular = !PER || s < nreg;
             const bool canon = regular ? e >= 0 : !(p.d.id[j] < idi);
@@ -236,6 +243,7 @@ __global__ void __launch_bounds__(128) k_neighbours(const Params p) {
                 v = MLH_FMAP_GHOST_SEARCH;
             }
             p.d.fmap[at] = v;
+          }
         }
         p.d.nown[i] = nown;
     }

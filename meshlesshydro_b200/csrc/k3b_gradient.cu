@@ -35,8 +35,11 @@ __device__ __forceinline__ void load_neighbour(const Params &p, int e, double *n
     }
 }
 
+#ifndef MLH_K3B_BLOCKS
+#define MLH_K3B_BLOCKS 4
+#endif
 template <int D, bool PER>
-__global__ void __launch_bounds__(128, 4) k_gradient_limit(const Params p) {
+__global__ void __launch_bounds__(128, MLH_K3B_BLOCKS) k_gradient_limit(const Params p) {
     constexpr int NF = D + 2;
     constexpr int PK1 = MLH_PK1(D);
     int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;

@@ -626,53 +626,96 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
     const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
     const int fs = p.d.face_start[i];
     bool over = false;
-    for (int s = 0; s < ntot; ++s) {
-        const size_t at = (size_t)s * p.ncap + i;
-        const unsigned v = p.d.fmap[at];
-        const int e = p.d.nnl[at];
-        const int j = e & MLH_NNL_IDX_MASK;
-        if (v & 2u) {
-            const int f = fs + (int)(v >> 2);
-            if (f < p.fcap) {
-                p.d.fa[f] = i | (int)((v & 1u) << 31); // bit 31: the partner is the canonical endpoint (lower original index)
-                p.d.fe[f] = e;
-            } else {
-                over = true;
-            }
-            continue;
+    // Four slots per trip: a partner-owned slot is a chain of dependent gathers (entry -> j's group start, mask and list
+    // length -> j's slot -> its face), latency-bound one at a time; the four chains of a trip are independent.
+    for (int s0 = 0; s0 < ntot; s0 += 4) {
+        unsigned v[4], g0[4];
+        unsigned long long nb[4];
+        int e[4], nrj[4], fsj[4];
+        bool fast[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int s = s0 + q < ntot ? s0 + q : ntot - 1;
+            const size_t at = (size_t)s * p.ncap + i;
+            v[q] = p.d.fmap[at];
+            e[q] = p.d.nnl[at];
         }
-        int t = -1;
-        if (!PER || s < nreg) {
-            const int li = (int)((v >> 2) & 0xFFFu), c = (int)(v >> 14);
-            const unsigned g0 = p.d.grp[(size_t)c * p.ncap + j];
-            const int nrj = p.d.noi[j];
-            if (!(g0 & 0x8000u) && li < 64) {
-                t = (int)g0 + __popcll(p.d.nbm[(size_t)c * p.ncap + j] & ((1ull << li) - 1ull));
-                if (t >= nrj || p.d.nnl[(size_t)t * p.ncap + j] != i) t = -1; // j's list was cut at max_interactions
-            } else { // crowded cell: scan j's list from the start of the group
-                for (int q = (int)(g0 & 0x7FFFu); q < nrj; ++q)
-                    if (p.d.nnl[(size_t)q * p.ncap + j] == i) {
-                        t = q;
-                        break;
-                    }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = e[q] & MLH_NNL_IDX_MASK;
+            const bool partner = !(v[q] & 2u) && (!PER || s0 + q < nreg);
+            fast[q] = false;
+            if (partner) {
+                const int c = (int)(v[q] >> 14);
+                g0[q] = p.d.grp[(size_t)c * p.ncap + j];
+                nb[q] = p.d.nbm[(size_t)c * p.ncap + j];
+                nrj[q] = p.d.noi[j];
+                fsj[q] = p.d.face_start[j];
+                fast[q] = !(g0[q] & 0x8000u) && (int)((v[q] >> 2) & 0xFFFu) < 64;
             }
-        } else {
-            const int want = i | (reverse_code((int)((unsigned)e >> MLH_NNL_IDX_BITS)) << MLH_NNL_IDX_BITS);
-            const int nrj = p.d.noi[j], ntj = nrj + p.d.noig[j];
-            for (int q = nrj; q < ntj; ++q)
-                if (p.d.nnl[(size_t)q * p.ncap + j] == want) {
-                    t = q;
-                    break;
+        }
+        int t[4];
+        unsigned vj[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            t[q] = -1;
+            if (fast[q]) {
+                const int j = e[q] & MLH_NNL_IDX_MASK;
+                const int li = (int)((v[q] >> 2) & 0xFFFu);
+                const int tt = (int)g0[q] + __popcll(nb[q] & ((1ull << li) - 1ull));
+                if (tt < nrj[q]) {
+                    t[q] = tt;
+                    vj[q] = p.d.fmap[(size_t)tt * p.ncap + j]; // owned by j: rank << 2 | 2 | sign
+                    if (p.d.nnl[(size_t)tt * p.ncap + j] != i) t[q] = -1; // j's list was cut at max_interactions
                 }
+            }
         }
-        unsigned res = MLH_FMAP_SKIP;
-        if (t >= 0) {
-            const unsigned vj = p.d.fmap[(size_t)t * p.ncap + j]; // owned by j: rank << 2 | 2 | sign
-            res = ((unsigned)(p.d.face_start[j] + (int)(vj >> 2)) << 2) | 1u;
-        } else {
-            over = true; // (MLH_F_MAX_INTERACTIONS is raised by K2 as well)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int s = s0 + q;
+            if (s >= ntot) break;
+            const size_t at = (size_t)s * p.ncap + i;
+            const int j = e[q] & MLH_NNL_IDX_MASK;
+            if (v[q] & 2u) {
+                const int f = fs + (int)(v[q] >> 2);
+                if (f < p.fcap) {
+                    p.d.fa[f] = i | (int)((v[q] & 1u) << 31); // bit 31: the partner is the canonical endpoint (lower original index)
+                    p.d.fe[f] = e[q];
+                } else {
+                    over = true;
+                }
+                continue;
+            }
+            int tq = t[q];
+            unsigned vjq = vj[q];
+            int fsjq = fsj[q];
+            if (!fast[q]) { // crowded cell or periodic image: scan j's list
+                if (!PER || s < nreg) {
+                    const int nr = p.d.noi[j];
+                    for (int k = (int)(g0[q] & 0x7FFFu); k < nr; ++k)
+                        if (p.d.nnl[(size_t)k * p.ncap + j] == i) {
+                            tq = k;
+                            break;
+                        }
+                } else {
+                    const int want = i | (reverse_code((int)((unsigned)e[q] >> MLH_NNL_IDX_BITS)) << MLH_NNL_IDX_BITS);
+                    const int nr = p.d.noi[j], nt = nr + p.d.noig[j];
+                    for (int k = nr; k < nt; ++k)
+                        if (p.d.nnl[(size_t)k * p.ncap + j] == want) {
+                            tq = k;
+                            break;
+                        }
+                }
+                if (tq >= 0) vjq = p.d.fmap[(size_t)tq * p.ncap + j];
+                fsjq = p.d.face_start[j];
+            }
+            unsigned res = MLH_FMAP_SKIP;
+            if (tq >= 0)
+                res = ((unsigned)(fsjq + (int)(vjq >> 2)) << 2) | 1u;
+            else
+                over = true; // (MLH_F_MAX_INTERACTIONS is raised by K2 as well)
+            p.d.fmap[at] = res;
         }
-        p.d.fmap[at] = res;
     }
     if (over) atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
 }
@@ -757,8 +800,10 @@ __device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid
 // ---------------------------------------------------------------------------------------------
 // K4a: one thread per (slot, particle)
 // ---------------------------------------------------------------------------------------------
+// resident blocks per SM (register cap): 3D needs 168 registers to run spill-free (3 blocks: 0.360 -> 0.339 ms at 61^3),
+// 2D fits 128 and gains from the fourth block (KH 1M 0.86 ms vs 1.04 ms at 3) -- A/B r01v, profiles/README.md
 #ifndef MLH_K4A_BLOCKS_PER_SM
-#define MLH_K4A_BLOCKS_PER_SM 4
+#define MLH_K4A_BLOCKS_PER_SM(D) ((D) == 3 ? 3 : 4)
 #endif
 #ifndef MLH_FUSE_SETUP
 #define MLH_FUSE_SETUP 0
@@ -767,7 +812,7 @@ __device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid
 // record is read once instead of twice.  Measured (A/B, profiles/README.md r01q): no gain at Sedov 61^3 (0.561 ms vs
 // 0.370 + 0.188 ms) and a loss at KH 1M (2.52 vs 0.98 + 1.36 ms) -- 3x the spills and a 75 KB instruction footprint.
 template <int D, bool PER, bool FUSE>
-__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM) k_face_states(const Params p, double *__restrict__ stage, int f0, int cstride, double dt_fixed, double dt_max,
+__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_face_states(const Params p, double *__restrict__ stage, int f0, int cstride, double dt_fixed, double dt_max,
                                                                                       double *__restrict__ pstar, double *__restrict__ qd, int *__restrict__ qi, int *__restrict__ qcount) {
     constexpr int NW = D + 2;
     constexpr int PK1 = MLH_PK1(D), PK2 = MLH_PK2(D);
@@ -1223,16 +1268,29 @@ __global__ void __launch_bounds__(128) k_flux_sum_update(const Params p, double 
     double acc[NW];
 #pragma unroll
     for (int nu = 0; nu < NW; ++nu) acc[nu] = 0.;
-    for (int s = 0; s < ntot; ++s) {
-        const unsigned v = p.d.fmap[(size_t)s * p.ncap + i];
-        if (v == MLH_FMAP_SKIP) continue;
-        const int f = (v & 2u) ? fs + (int)(v >> 2) : (int)(v >> 2);
-        if (f >= p.fcap) continue; // face capacity exceeded (flag raised by k_face_index)
-        double Fr[FREC];
-        load_packed<FREC>(p.d.F + (size_t)f * FREC, Fr);
-        const double sgn = (v & 1u) ? -1. : 1.;
+    // four slots per trip: the map entries and then the four flux records are fetched together (independent gathers),
+    // the sums still run in list order
+    for (int s0 = 0; s0 < ntot; s0 += 4) {
+        unsigned v[4];
+        double Fr[4][FREC];
 #pragma unroll
-        for (int nu = 0; nu < NW; ++nu) acc[nu] += sgn * Fr[nu];
+        for (int q = 0; q < 4; ++q) v[q] = s0 + q < ntot ? p.d.fmap[(size_t)(s0 + q) * p.ncap + i] : MLH_FMAP_SKIP;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int f = (v[q] & 2u) ? fs + (int)(v[q] >> 2) : (int)(v[q] >> 2);
+            if (v[q] == MLH_FMAP_SKIP || f >= p.fcap) { // no face / face capacity exceeded (flag raised by k_face_index)
+                v[q] = MLH_FMAP_SKIP;
+                continue;
+            }
+            load_packed<FREC>(p.d.F + (size_t)f * FREC, Fr[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (v[q] == MLH_FMAP_SKIP) continue;
+            const double sgn = (v[q] & 1u) ? -1. : 1.;
+#pragma unroll
+            for (int nu = 0; nu < NW; ++nu) acc[nu] += sgn * Fr[q][nu];
+        }
     }
     if (p.debug_capture) {
         p.d.flux[0][i] = acc[0];
@@ -1317,7 +1375,8 @@ int launch_chunks(mlh_ctx *c, double dt_fixed, double dt_max) {
     // at KH 1M; finish holds 6 blocks/SM by registers: one clean wave is best in 3D (0.157 -> 0.125 ms), 8 in 2D)
     static const int g_setup = getenv("MLH_GRID_SETUP") ? atoi(getenv("MLH_GRID_SETUP")) : 16;
     static const int g_finish = getenv("MLH_GRID_FINISH") ? atoi(getenv("MLH_GRID_FINISH")) : (D == 3 ? 6 : 8);
-    static const int g_states = getenv("MLH_GRID_STATES") ? atoi(getenv("MLH_GRID_STATES")) : 8;
+    // K4a: two clean waves of its resident blocks (3 per SM in 3D, 4 in 2D): 0.339 -> 0.309 ms at 61^3 (r01w)
+    static const int g_states = getenv("MLH_GRID_STATES") ? atoi(getenv("MLH_GRID_STATES")) : 2 * MLH_K4A_BLOCKS_PER_SM(D);
     cudaStream_t st = c->stream;
     // The face count lives on the device (face_start[own_end]); without a host round trip the chunk loop covers the
     // face CAPACITY and the kernels of chunks beyond the last face return at once.  One chunk in the usual case.
