@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define MLH_ABI_VERSION 1
+#define MLH_ABI_VERSION 2
 
 /* status codes */
 #define MLH_OK 0
@@ -68,6 +68,9 @@ typedef struct {
     int symmetric_seam;       /* 1: a periodic-seam pair is kept iff EITHER side passes the cutoff
                                  test (conservative; deviates from the reference's sets, quirk Q9) */
     int debug_capture;        /* 1: also store pre-limiter gradients and per-particle flux sums */
+    int first_order_quad_point; /* FIRST_ORDER_QUAD_POINT parameter.h:55: 1 = face at the midpoint (every shipped parameter
+                                 file), 0 = at x_i + kernelSize/4 (x_j - x_i) (Particles.cpp:1358-1359,1514-1537,1555-1563) */
+    int reserved0;            /* keeps the doubles 8-byte aligned; must be 0 */
     double cfl;               /* CFL    parameter.h:18 */
     double beta;              /* BETA   parameter.h:31 */
     double psi1, psi2;        /* PSI_1, PSI_2 parameter.h:35-36 */

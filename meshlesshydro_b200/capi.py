@@ -25,7 +25,8 @@ c_ip = C.POINTER(C.c_int)
 class MlhConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "dim", "periodic", "max_interactions", "slope_limiting", "pairwise_limiter", "meshless_finite_mass",
-        "move_particles", "abs_mode", "q13_mode", "q3_mode", "symmetric_seam", "debug_capture")] + \
+        "move_particles", "abs_mode", "q13_mode", "q3_mode", "symmetric_seam", "debug_capture", "first_order_quad_point",
+        "reserved0")] + \
         [(n, C.c_double) for n in ("cfl", "beta", "psi1", "psi2", "kernel_size", "gamma")] + \
         [("box", C.c_double * 6), ("device", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("capacity", C.c_long),
          ("stage_bytes", C.c_long)]

@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(128, MLH_K3B_BLOCKS) k_gradient_limit(const Pa
                 double xijxi[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    const double xij = __dmul_rn(__dadd_rn(xi[k], nb[k]), .5); // (x_i + x_j)/2 (exact either way), FIRST_ORDER_QUAD_POINT, :1355-1356
+                    // FIRST_ORDER_QUAD_POINT: (x_i + x_j)/2 (`*.5` is exact like `/2.`), :1355-1356; else :1358-1359,1369
+                    const double xij = p.quad_h4 ? __dadd_rn(xi[k], __dmul_rn(p.h4, __dsub_rn(nb[k], xi[k])))
+                                                 : __dmul_rn(__dadd_rn(xi[k], nb[k]), .5);
                     xijxi[k] = __dsub_rn(xij, xi[k]);
                 }
 #pragma unroll

@@ -939,12 +939,27 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_fac
         // ---- boosted, reconstructed, predicted states (Particles.cpp:1498-1721; ghosts :2546-2672) ----
         double xjxi[3], xijxi[D], xijxj[D], vF[D];
         xjxi[2] = 0.; // quirk Q13 (ZERO_Z): never written in the first-order 3D branch
+        if (!p.quad_h4) { // FIRST_ORDER_QUAD_POINT 1: face at the midpoint (:1504-1512,1526-1529,1550-1553)
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            if (k < 2 || p.q13_mode == MLH_Q13_GEOMETRIC) xjxi[k] = xbi[k] - xa[k];
-            xijxj[k] = .5 * (xa[k] - xbi[k]);
-            xijxi[k] = .5 * (xbi[k] - xa[k]);
-            vF[k] = p.move_particles ? (va[k] + vb[k]) / 2. : 0.;
+            for (int k = 0; k < D; ++k) {
+                if (k < 2 || p.q13_mode == MLH_Q13_GEOMETRIC) xjxi[k] = xbi[k] - xa[k];
+                xijxj[k] = .5 * (xa[k] - xbi[k]);
+                xijxi[k] = .5 * (xbi[k] - xa[k]);
+                vF[k] = p.move_particles ? (va[k] + vb[k]) / 2. : 0.;
+            }
+        } else { // FIRST_ORDER_QUAD_POINT 0: face at x_a + h/4 (x_b - x_a), frame velocity interpolated to it (:1514-1523,1531-1537,1556-1563)
+            double dotProd = 0., dSqr = 0.;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                xjxi[k] = xbi[k] - xa[k];
+                const double xij = xa[k] + p.h4 * xjxi[k];
+                xijxi[k] = xij - xa[k];
+                xijxj[k] = xij - xbi[k];
+                dotProd += xijxi[k] * xjxi[k];
+                dSqr += xjxi[k] * xjxi[k];
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) vF[k] = p.move_particles ? va[k] + (vb[k] - va[k]) * dotProd / dSqr : 0.;
         }
         Wa[0] = rhoa;
         Wb[0] = rhob;

@@ -260,6 +260,7 @@ void mlh_default_config(mlh_config *cfg) {
     cfg->abs_mode = MLH_ABS_FABS;
     cfg->q13_mode = MLH_Q13_ZERO_Z;
     cfg->q3_mode = MLH_Q3_REFERENCE;
+    cfg->first_order_quad_point = 1; // :55
     cfg->cfl = .2;           // :18
     cfg->beta = 4.;          // :31
     cfg->psi1 = .5;
@@ -319,6 +320,8 @@ int mlh_create(const mlh_config *cfg, mlh_ctx **out) {
     p.q3_mode = cfg->q3_mode;
     p.symmetric_seam = cfg->symmetric_seam;
     p.debug_capture = cfg->debug_capture;
+    p.quad_h4 = cfg->first_order_quad_point ? 0 : 1;
+    p.h4 = cfg->kernel_size / 4.; // `kernelSize/4.` of Particles.cpp:1358,1515
     p.h = cfg->kernel_size;
     p.hSqr = cfg->kernel_size * cfg->kernel_size; // Particles.cpp:334
     p.gamma = cfg->gamma;

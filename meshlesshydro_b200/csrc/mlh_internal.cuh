@@ -94,6 +94,8 @@ struct Params {
     int max_ni;
     int fcap;       // face capacity (fa, fe, F)
     int slope_limiting, pairwise, mfm, move_particles, abs_mode, q13_mode, q3_mode, symmetric_seam, debug_capture;
+    int quad_h4;    // FIRST_ORDER_QUAD_POINT 0: face at x_i + h4 (x_j - x_i), h4 = kernelSize/4 (a FACTOR, as in the reference)
+    double h4;
     double h, hSqr, gamma, cfl, beta, psi1, psi2;
     double h2, sigma, sigma4; // cubic spline: h/2, normalisation, normalisation/4 (Particles.cpp:10-15)
     RsConsts rs;

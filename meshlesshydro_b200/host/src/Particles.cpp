@@ -175,6 +175,7 @@ void Particles::ensure(int target) {
         cfg.pairwise_limiter = PAIRWISE_LIMITER;
         cfg.meshless_finite_mass = MESHLESS_FINITE_MASS;
         cfg.move_particles = MOVE_PARTICLES;
+        cfg.first_order_quad_point = FIRST_ORDER_QUAD_POINT;
         cfg.abs_mode = envInt("MLH_ABS_MODE", MLH_ABS_FABS);
         cfg.q13_mode = envInt("MLH_Q13_MODE", MLH_Q13_ZERO_Z);
         cfg.q3_mode = envInt("MLH_Q3_MODE", MLH_Q3_REFERENCE);

@@ -114,6 +114,19 @@ def sedov(n_side, jitter=0.05):
     )
 
 
+def warm_blob_3d(n_side):
+    """Smooth 3D test state on the Sedov particle arrangement: u = 1 + 0.2 exp(-r^2/0.05), a gentle shear flow.
+    Not one of the reference's cases -- for variants that the blast wave turns into NaN in the reference itself
+    (FIRST_ORDER_QUAD_POINT 0 extrapolates the neighbour's state over ~the full separation)."""
+    ic = sedov(n_side)
+    r2 = ic["x"] ** 2 + ic["y"] ** 2 + ic["z"] ** 2
+    ic["u"] = 1.0 + 0.2 * np.exp(-r2 / 0.05)
+    ic["vx"] = 0.1 * np.sin(2.0 * np.pi * ic["y"])
+    ic["vy"] = 0.05 * np.cos(2.0 * np.pi * ic["z"])
+    ic["vz"] = 0.05 * np.sin(2.0 * np.pi * ic["x"])
+    return ic
+
+
 def fluid_block(n_side, h_over_dx=3.5, jitter=0.0):
     """fluid-block 2D (``generateIC.py -t``): lattice in [-.5,.5)^2, v = 0, rho = 1, u = 1."""
     N = n_side * n_side

@@ -646,7 +646,10 @@ static void slope_limiter(Orc *o, const double *f, double *grad, const double *f
         for (jn = 0; jn < o->noi[i]; ++jn) {
             int j = o->nnl[(size_t)i * o->cfg.max_ni + jn];
             for (a = 0; a < D; ++a) {
-                xij[a] = (o->x[a][i] + o->x[a][j]) / 2.;
+                if (o->cfg.quad_point_h4) /* :1358-1359,1369 */
+                    xij[a] = o->x[a][i] + o->cfg.h / 4. * (o->x[a][j] - o->x[a][i]);
+                else
+                    xij[a] = (o->x[a][i] + o->x[a][j]) / 2.;
                 xijxi[a] = xij[a] - o->x[a][i];
             }
             if (psiMaxNgb < f[j]) psiMaxNgb = f[j];
@@ -659,7 +662,10 @@ static void slope_limiter(Orc *o, const double *f, double *grad, const double *f
             for (jn = 0; jn < o->noiG[i]; ++jn) {
                 int j = o->nnlG[(size_t)i * o->cfg.max_gi + jn];
                 for (a = 0; a < D; ++a) {
-                    xij[a] = (o->x[a][i] + o->gx[a][j]) / 2.;
+                    if (o->cfg.quad_point_h4) /* :1391-1392,1402 */
+                        xij[a] = o->x[a][i] + o->cfg.h / 4. * (o->gx[a][j] - o->x[a][i]);
+                    else
+                        xij[a] = (o->x[a][i] + o->gx[a][j]) / 2.;
                     xijxi[a] = xij[a] - o->x[a][i];
                 }
                 if (psiMaxNgb < fGhost[j]) psiMaxNgb = fGhost[j];
@@ -774,16 +780,26 @@ static void riemann_states(Orc *o, double dt) {
             const double *gi[5], *gj[5];
             xjxi[0] = o->x[0][j] - o->x[0][i];
             xjxi[1] = o->x[1][j] - o->x[1][i];
-            if (D == 3 && o->cfg.q13_mode == 1) xjxi[2] = o->x[2][j] - o->x[2][i];
-            for (a = 0; a < D; ++a) {
-                xijxj[a] = .5 * (o->x[a][i] - o->x[a][j]);
-                xijxi[a] = .5 * (o->x[a][j] - o->x[a][i]);
+            if (D == 3 && (o->cfg.q13_mode == 1 || o->cfg.quad_point_h4)) xjxi[2] = o->x[2][j] - o->x[2][i]; /* :1531 */
+            if (o->cfg.quad_point_h4) { /* FIRST_ORDER_QUAD_POINT 0, :1514-1523,1531-1537 */
+                for (a = 0; a < D; ++a) {
+                    double xij = o->x[a][i] + o->cfg.h / 4. * xjxi[a];
+                    xijxi[a] = xij - o->x[a][i];
+                    xijxj[a] = xij - o->x[a][j];
+                }
+            } else {
+                for (a = 0; a < D; ++a) {
+                    xijxj[a] = .5 * (o->x[a][i] - o->x[a][j]);
+                    xijxi[a] = .5 * (o->x[a][j] - o->x[a][i]);
+                }
             }
-            for (a = 0; a < D; ++a) {
-                if (o->cfg.move_particles)
-                    vF[a] = (o->v[a][i] + o->v[a][j]) / 2.;
-                else
-                    vF[a] = 0.;
+            if (!o->cfg.move_particles) {
+                for (a = 0; a < D; ++a) vF[a] = 0.;
+            } else if (o->cfg.quad_point_h4) { /* :1556-1563 */
+                double dotProd = dotp(xijxi, xjxi, D), dSqr = dotp(xjxi, xjxi, D);
+                for (a = 0; a < D; ++a) vF[a] = o->v[a][i] + (o->v[a][j] - o->v[a][i]) * dotProd / dSqr;
+            } else {
+                for (a = 0; a < D; ++a) vF[a] = (o->v[a][i] + o->v[a][j]) / 2.;
             }
             WR[0] = o->rho[i];
             WL[0] = o->rho[j];
@@ -866,6 +882,20 @@ static void riemann_states_ghosts(Orc *o, double dt) {
             double *WR = &o->WijRG[iW * NW], *WL = &o->WijLG[iW * NW], *vF = &o->vFrameG[iW * D];
             double xijxi[3], xijxj[3], viDiv, vjDiv;
             const double *gi[5], *gj[5];
+            if (o->cfg.quad_point_h4) { /* :2563-2570, 2602-2611 */
+                double xjxi[3], dotProd, dSqr;
+                for (a = 0; a < D; ++a) {
+                    double xij;
+                    xjxi[a] = o->gx[a][j] - o->x[a][i];
+                    xij = o->x[a][i] + o->cfg.h / 4. * xjxi[a];
+                    xijxi[a] = xij - o->x[a][i];
+                    xijxj[a] = xij - o->gx[a][j];
+                }
+                dotProd = dotp(xijxi, xjxi, D);
+                dSqr = dotp(xjxi, xjxi, D);
+                for (a = 0; a < D; ++a)
+                    vF[a] = o->cfg.move_particles ? o->v[a][i] + (o->gv[a][j] - o->v[a][i]) * dotProd / dSqr : 0.;
+            } else
             for (a = 0; a < D; ++a) {
                 xijxj[a] = .5 * (o->x[a][i] - o->gx[a][j]);
                 xijxi[a] = .5 * (o->gx[a][j] - o->x[a][i]);

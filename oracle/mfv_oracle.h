@@ -35,7 +35,8 @@ typedef struct {
     int abs_mode;       /* quirk Q1: 0 = INT_TRUNC (int abs(int), g++/libstdc++), 1 = FABS */
     int q13_mode;       /* quirk Q13: 0 = ZERO_Z (xjxi[2] reads as 0), 1 = GEOMETRIC       */
     int q3_mode;        /* quirk Q3: 0 = as the reference (vz[i] on the j side), 1 = fixed */
-    int reserved;
+    int quad_point_h4;  /* 1 = FIRST_ORDER_QUAD_POINT 0: quadrature point x_i + h/4 (x_j - x_i) (parameter.h:55,
+                           Particles.cpp:1358-1359,1514-1537,1555-1563); 0 = the midpoint (all shipped parameter files) */
     double cfl;         /* CFL   (parameter.h:18) */
     double beta;        /* BETA  (parameter.h:31) */
     double psi1, psi2;  /* PSI_1, PSI_2 (parameter.h:35-36) */

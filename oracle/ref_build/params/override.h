@@ -17,6 +17,10 @@
 #undef PAIRWISE_LIMITER
 #define PAIRWISE_LIMITER MLH_REF_PAIRWISE
 #endif
+#ifdef MLH_REF_FOQP
+#undef FIRST_ORDER_QUAD_POINT
+#define FIRST_ORDER_QUAD_POINT MLH_REF_FOQP
+#endif
 #ifdef MLH_REF_MAXNI
 #undef MAX_NUM_INTERACTIONS
 #define MAX_NUM_INTERACTIONS MLH_REF_MAXNI

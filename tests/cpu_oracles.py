@@ -24,7 +24,7 @@ INT_FIELDS = {"cell", "noi", "nnl", "noiGhosts", "nnlGhosts", "ghostMap", "ghost
 
 class OrcConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("dim", "periodic", "max_ni", "max_gi", "slope_limiting", "pairwise", "mfm",
-                                       "move_particles", "abs_mode", "q13_mode", "q3_mode", "reserved")] + \
+                                       "move_particles", "abs_mode", "q13_mode", "q3_mode", "quad_point_h4")] + \
                [(n, C.c_double) for n in ("cfl", "beta", "psi1", "psi2", "h", "gamma")] + [("box", C.c_double * 6)]
 
 
@@ -51,6 +51,7 @@ def make_config(preset, h, gamma, box=None, abs_mode=0, q13_mode=0, q3_mode=0, *
     cfg.slope_limiting, cfg.pairwise = p["slope_limiting"], p["pairwise"]
     cfg.mfm, cfg.move_particles = p.get("mfm", 0), p.get("move_particles", 1)
     cfg.abs_mode, cfg.q13_mode, cfg.q3_mode = abs_mode, q13_mode, q3_mode
+    cfg.quad_point_h4 = p.get("quad_point_h4", 0)
     cfg.cfl, cfg.beta, cfg.psi1, cfg.psi2 = p["cfl"], p["beta"], p["psi1"], p["psi2"]
     cfg.h, cfg.gamma = h, gamma
     for k in range(6):

@@ -30,7 +30,7 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_defaults():
     lib = capi.load_library()
-    assert lib.mlh_abi_version() == 1
+    assert lib.mlh_abi_version() == 2
     cfg = capi.default_config()
     # demonstrator/include/parameter.h values
     assert (cfg.dim, cfg.periodic, cfg.slope_limiting, cfg.pairwise_limiter, cfg.move_particles) == (2, 1, 1, 1, 1)

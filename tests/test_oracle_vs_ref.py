@@ -15,6 +15,10 @@ CASES = [
     ("fb_lattice_fabs", lambda: IC.fluid_block(36), "fb2d", "fb2d_fabs", 1, 0.0),
     ("sedov", lambda: IC.sedov(14), "sedov3d", "sedov3d", 0, 1e-10),
     ("sedov_fabs", lambda: IC.sedov(14), "sedov3d", "sedov3d_fabs", 1, 1e-10),
+    # FIRST_ORDER_QUAD_POINT 0 (quadrature point x_i + h/4 (x_j - x_i)); reference built with that switch
+    ("kh_jitter_foqp0", lambda: IC.kelvin_helmholtz(40, lattice=True, jitter=0.2), "kh2d", "kh2d_foqp0", 1, 0.0),
+    ("fb_jitter_foqp0", lambda: IC.fluid_block(40, jitter=0.05), "fb2d", "fb2d_foqp0", 1, 0.0),
+    ("blob3d_foqp0", lambda: IC.warm_blob_3d(14), "sedov3d", "sedov3d_foqp0", 1, 1e-10),
 ]
 
 
@@ -23,7 +27,8 @@ def test_restatement_equals_reference_sources(name, factory, preset, variant, ab
     if not Reference.available(variant):
         pytest.skip("oracle/_ref/libref_%s.so not built" % variant)
     ic = factory()
-    orc = Oracle(make_config(preset, ic["h"], ic["gamma"], ic.get("box"), abs_mode=abs_mode), ic)
+    over = {"quad_point_h4": 1} if variant.endswith("_foqp0") else {}
+    orc = Oracle(make_config(preset, ic["h"], ic["gamma"], ic.get("box"), abs_mode=abs_mode, **over), ic)
     ref = Reference(variant, ic)
     for step in range(3):
         dt_o, dt_r = orc.step(), ref.step()
