@@ -57,14 +57,31 @@ __device__ __forceinline__ double rs_min(double a, double b) { return (b < a) ? 
 __device__ __noinline__ double mlh_pow(double x, double y) { return x == 0. ? 0. : exp(y * log(x)); }
 
 // x^((gamma-1)/(2 gamma)), the one power the root finder evaluates every iteration.  For gamma = 5/3 and 7/5 the
-// exponent is 1/5 resp. 1/7: z = x^(-1/n) by two division-free Newton steps z <- z + z (1 - x z^n)/n from a
-// single-precision seed (relative error 5e-7 -> 7e-13 -> 2e-24, i.e. rounding-limited), then x^(1/n) = x z^(n-1).
-// ~20 FP64 instructions instead of ~130 for exp(y log x); x = 1 gives exactly 1 (as pow does), which keeps
-// f(P) = 0 exact on faces between identical states.  Other gamma, and x outside [1e-30, 1e30], take the generic path.
+// exponent is 1/5 resp. 1/7: z ~ x^(-1/n) from a single-precision seed (relative error e < 1e-6), residual
+// r = 1 - x z^n, and ONE third-order correction z <- z (1 + r/n + (n+1)/(2 n^2) r^2) -- the first terms of
+// (1 - r)^(-1/n); the remainder 0.09 r^3 (r ~ n e) is < 1e-17.  Then x^(1/n) = x z^(n-1).
+// ~10 FP64 instructions on a short dependency chain (two Newton steps took 15) instead of ~130 for exp(y log x);
+// x = 1 gives exactly 1 (as pow does), which keeps f(P) = 0 exact on faces between identical states.  Other gamma,
+// and x outside [1e-12, 1e12] (where the float seed is no longer good enough), take the generic path.
+// ONE_STEP = false (setup / finish kernels): the earlier form with two division-free Newton steps
+// z <- z + z (1 - x z^n)/n, same accuracy; kept there because the shorter form changes their register allocation
+// (setup 54 -> 84) and with it the occupancy their grids are tuned for (A/B r01x: finish 0.125 -> 0.188 ms).
+template <bool ONE_STEP>
 __device__ __forceinline__ double rs_root_pow(const RsConsts &c, double x) {
     const int n = c.root_n;
-    if (n == 0 || !(x > 1e-30 && x < 1e30)) return mlh_pow(x, c.gm1d2g);
     const double rn = c.gm1d2g; // 1/n
+    if (ONE_STEP) {
+        if (n == 0 || !(x > 1e-12 && x < 1e12)) return mlh_pow(x, c.gm1d2g);
+        const double c2 = 0.5 * rn * (rn + 1.);
+        double z = (double)exp2f(-__log2f((float)x) * (float)rn);
+        const double z2 = z * z, z4 = z2 * z2;
+        const double zn = (n == 5) ? z4 * z : z4 * z2 * z;
+        const double r = fma(-x, zn, 1.);
+        z = fma(z, r * fma(c2, r, rn), z);
+        const double y2 = z * z, y4 = y2 * y2;
+        return x * ((n == 5) ? y4 : y4 * y2);
+    }
+    if (n == 0 || !(x > 1e-30 && x < 1e30)) return mlh_pow(x, c.gm1d2g);
     double z = (double)exp2f(-__log2f((float)x) * (float)rn);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -95,11 +112,11 @@ __device__ __forceinline__ void rs_eval2(const RsConsts &c, double rhoL, double 
     if (!shL || !shR) {
         const bool firstL = !shL;
         const double r1 = RECIP ? Ps * (firstL ? iPL : iPR) : Ps / (firstL ? PL : PR);
-        const double w1 = rs_root_pow(c, r1);
+        const double w1 = rs_root_pow<RECIP>(c, r1);
         if (firstL) { wL = w1; rL = r1; } else { wR = w1; rR = r1; }
         if (!shL && !shR) {
             rR = RECIP ? Ps * iPR : Ps / PR;
-            wR = rs_root_pow(c, rR);
+            wR = rs_root_pow<RECIP>(c, rR);
         }
     }
     if (shL || shR) {
@@ -256,7 +273,7 @@ __device__ __forceinline__ void rs_iter_update(RsIter &it, double s, double fs, 
 // both kinds anyway, so the divergent version executed all four paths with half-empty warps (profiles/r01k); here the
 // two sides are independent instruction streams that overlap in the FP64 pipe.
 __device__ __forceinline__ double rs_f_nobranch(const RsConsts &c, const RsProblem &q, double Ps) {
-    const double wL = rs_root_pow(c, Ps * q.iPL), wR = rs_root_pow(c, Ps * q.iPR);
+    const double wL = rs_root_pow<true>(c, Ps * q.iPL), wR = rs_root_pow<true>(c, Ps * q.iPR);
     const double qL = c.sqrt_tdgp1 * rsqrt(q.rhoL * (Ps + c.gm1dgp1 * q.PL));
     const double qR = c.sqrt_tdgp1 * rsqrt(q.rhoR * (Ps + c.gm1dgp1 * q.PR));
     const double fL = (Ps > q.PL) ? (Ps - q.PL) * qL : c.tdgm1 * q.aL * (wL - 1.);
@@ -357,6 +374,8 @@ __device__ __noinline__ int rs_solve_vacuum(const RsConsts c, double rhoL, doubl
 // (k_face_riemann): setup (sound speeds, vacuum test, initial guess, f at 0 and at the guess), root (Newton /
 // Brent for P*), sample (star state at x/t = 0).  Together they are RiemannSolver::solve (Riemann.cpp:93-94).
 
+// (k_face_setup / k_face_finish pin their register budgets with __launch_bounds__: ptxas' natural allocation moved
+// between 54 and 84 registers with unrelated edits, and the persistent grids are sized for a given occupancy)
 // returns false if the (generated) vacuum path must be taken
 __device__ __forceinline__ bool rs_setup(const RsConsts &c, double rhoL, double uL, double PL, double rhoR, double uR, double PR,
                                          RsProblem &q) {
@@ -1081,7 +1100,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_fac
 
 
 template <int D>
-__global__ void __launch_bounds__(MLH_FACE_TILE) k_face_setup(const Params p, const double *__restrict__ stage, double *__restrict__ pstar,
+__global__ void __launch_bounds__(MLH_FACE_TILE, 8) k_face_setup(const Params p, const double *__restrict__ stage, double *__restrict__ pstar,
                                                               double *__restrict__ qd, int *__restrict__ qi, int *__restrict__ qcount,
                                                               int f0, int cstride) {
     constexpr int NW = D + 2;
@@ -1222,8 +1241,13 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_i
     }
 }
 
+// 8 resident blocks (<= 64 registers, a few spilled values): HBM-bound streaming, more loads in flight win
+// (r01z: KH 1M 0.78 -> 0.71 ms, 61^3 0.126 -> 0.123 ms against 6 blocks at 80 registers)
+#ifndef MLH_FINISH_BLOCKS
+#define MLH_FINISH_BLOCKS 8
+#endif
 template <int D>
-__global__ void __launch_bounds__(MLH_FACE_TILE) k_face_finish(const Params p, const double *__restrict__ stage, const double *__restrict__ pstar,
+__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_FINISH_BLOCKS) k_face_finish(const Params p, const double *__restrict__ stage, const double *__restrict__ pstar,
                                                                int f0, int cstride) {
     constexpr int NW = D + 2;
     constexpr int FREC = MLH_FREC(D);
@@ -1386,10 +1410,10 @@ int launch_chunks(mlh_ctx *c, double dt_fixed, double dt_max) {
     const int chunk = c->stage_chunk;
     const int grid_persistent = c->num_sms * 8;
     // blocks per SM of the streaming face kernels (setup / finish): tunable for A/B runs
-    // (tools/grid_sweep.sh, profiles/README.md r01t: setup 8 -> 16 blocks/SM 0.193 -> 0.157 ms at 61^3 and 1.36 -> 1.31 ms
-    // at KH 1M; finish holds 6 blocks/SM by registers: one clean wave is best in 3D (0.157 -> 0.125 ms), 8 in 2D)
+    // persistent grids = two clean waves of the blocks each kernel keeps resident (register budgets pinned by
+    // __launch_bounds__); sweeps: tools/grid_sweep.sh, profiles/README.md r01t / r01w / r01z
     static const int g_setup = getenv("MLH_GRID_SETUP") ? atoi(getenv("MLH_GRID_SETUP")) : 16;
-    static const int g_finish = getenv("MLH_GRID_FINISH") ? atoi(getenv("MLH_GRID_FINISH")) : (D == 3 ? 6 : 8);
+    static const int g_finish = getenv("MLH_GRID_FINISH") ? atoi(getenv("MLH_GRID_FINISH")) : 2 * MLH_FINISH_BLOCKS;
     // K4a: two clean waves of its resident blocks (3 per SM in 3D, 4 in 2D): 0.339 -> 0.309 ms at 61^3 (r01w)
     static const int g_states = getenv("MLH_GRID_STATES") ? atoi(getenv("MLH_GRID_STATES")) : 2 * MLH_K4A_BLOCKS_PER_SM(D);
     cudaStream_t st = c->stream;
