@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(128) k_density_matrix(const Params p) {
 #pragma unroll
     for (int k = 0; k < D; ++k) xi[k] = p.d.x[k][i];
     const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
-    // omega: regular terms, then the self term, then the image terms
+    // omega: regular terms, then the self term, then the image terms.  (Keeping the kernel values of this sweep in
+    // shared memory for the matrix sweep LOST, 0.100 -> 0.142 ms at 61^3: 32 KB per block is carved out of the L1 that
+    // serves the neighbour gathers -- profiles/README.md r02a.)
     // list entries are read two visits ahead and (2D) the next neighbour's coordinates prefetched into L1: each visit is
     // an entry load followed by a dependent gather.  Measured r01t: KH 1M 0.546 -> 0.482 ms; in 3D the third prefetch per
     // visit cost more than it hid (0.129 -> 0.133 ms), so only the entry pipeline is kept there.

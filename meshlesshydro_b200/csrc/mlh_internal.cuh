@@ -233,6 +233,20 @@ __device__ __forceinline__ void neighbour_geometry(const Params &p, const double
     }
     *r = sqrt(dist_sqr_exact<D>(s));
 }
+// the displacement alone
+template <int D, bool PER>
+__device__ __forceinline__ void neighbour_delta(const Params &p, const double *xi, int e, double *d) {
+    const int j = e & MLH_NNL_IDX_MASK;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double xj = p.d.x[k][j];
+        if (PER) {
+            int ck = (e >> (MLH_NNL_IDX_BITS + 2 * k)) & 3;
+            xj = image_coord(xj, ck, p.grid.bmin[k], p.grid.bmax[k]);
+        }
+        d[k] = __dsub_rn(xj, xi[k]);
+    }
+}
 
 
 // Bounding box of Particles::getDomainLimits (Particles.cpp:228-267): per-thread running min / max (max already
