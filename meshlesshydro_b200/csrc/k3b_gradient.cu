@@ -35,11 +35,13 @@ __device__ __forceinline__ void load_neighbour(const Params &p, int e, double *n
     }
 }
 
+// resident blocks per SM: the pipelined record (second register set) fits 128 registers in 2D; 3D needs 162 to stay
+// spill-free (A/B r02c: 0.190 -> 0.181 ms at 61^3 with 3 blocks, 0.200 ms with 4 and spills; KH 1M 0.99 -> 0.83 ms)
 #ifndef MLH_K3B_BLOCKS
-#define MLH_K3B_BLOCKS 4
+#define MLH_K3B_BLOCKS(D) ((D) == 3 ? 3 : 4)
 #endif
 template <int D, bool PER>
-__global__ void __launch_bounds__(128, MLH_K3B_BLOCKS) k_gradient_limit(const Params p) {
+__global__ void __launch_bounds__(128, MLH_K3B_BLOCKS(D)) k_gradient_limit(const Params p) {
     constexpr int NF = D + 2;
     constexpr int PK1 = MLH_PK1(D);
     int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,11 +80,19 @@ __global__ void __launch_bounds__(128, MLH_K3B_BLOCKS) k_gradient_limit(const Pa
         // list entries are fetched one visit ahead of the record gather (an L1 prefetch of the next record on top of
         // that cost more LSU issue than it hid: 0.199 -> 0.216 ms at 61^3, profiles/README.md r01t)
         int e_next = ntot > 0 ? p.d.nnl[i] : 0;
+        // software pipeline: the record of visit s+1 is requested before visit s is computed (the gather latency was the
+        // largest stall of both sweeps, profiles/r02b); its list entry was read a visit earlier
+        double nbn[PK1];
+        int e_next2 = ntot > 1 ? p.d.nnl[(size_t)p.ncap + i] : 0;
+        if (ntot > 0) load_neighbour<D, PER>(p, e_next, nbn);
+#pragma unroll 2
         for (int s = 0; s < ntot; ++s) {
-            const int e = e_next;
-            if (s + 1 < ntot) e_next = p.d.nnl[(size_t)(s + 1) * p.ncap + i];
             double nb[PK1];
-            load_neighbour<D, PER>(p, e, nb);
+#pragma unroll
+            for (int k = 0; k < PK1; ++k) nb[k] = nbn[k];
+            e_next = e_next2;
+            if (s + 2 < ntot) e_next2 = p.d.nnl[(size_t)(s + 2) * p.ncap + i];
+            if (s + 1 < ntot) load_neighbour<D, PER>(p, e_next, nbn);
             double d[3], sd[3];
 #pragma unroll
             for (int k = 0; k < D; ++k) {
@@ -133,11 +143,16 @@ __global__ void __launch_bounds__(128, MLH_K3B_BLOCKS) k_gradient_limit(const Pa
             minMid[f] = DBL_MAX;
         }
         e_next = ntot > 0 ? p.d.nnl[i] : 0;
+        e_next2 = ntot > 1 ? p.d.nnl[(size_t)p.ncap + i] : 0;
+        if (p.slope_limiting && ntot > 0) load_neighbour<D, PER>(p, e_next, nbn);
+#pragma unroll 2
         for (int s = 0; p.slope_limiting && s < ntot; ++s) {
-            const int e = e_next;
-            if (s + 1 < ntot) e_next = p.d.nnl[(size_t)(s + 1) * p.ncap + i];
             double nb[PK1];
-            load_neighbour<D, PER>(p, e, nb);
+#pragma unroll
+            for (int k = 0; k < PK1; ++k) nb[k] = nbn[k];
+            e_next = e_next2;
+            if (s + 2 < ntot) e_next2 = p.d.nnl[(size_t)(s + 2) * p.ncap + i];
+            if (s + 1 < ntot) load_neighbour<D, PER>(p, e_next, nbn);
             {
                 double xijxi[D];
 #pragma unroll

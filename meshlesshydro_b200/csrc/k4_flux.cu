@@ -879,6 +879,9 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_fac
         double A1[PK1], B1[PK1]; // packed records: x, v, rho, P, cs, omega
         load_packed<PK1>(p.d.pk1 + (size_t)ia * PK1, A1);
         load_packed<PK1>(p.d.pk1 + (size_t)ib * PK1, B1);
+        double A2[PK2], B2[PK2]; // packed records: Binv, limited gradients (W order) -- requested together with A1/B1
+        load_packed<PK2>(p.d.pk2 + (size_t)ia * PK2, A2);
+        load_packed<PK2>(p.d.pk2 + (size_t)ib * PK2, B2);
         const double *xa = A1, *xb = B1, *va = A1 + D, *vb = B1 + D;
         const double rhoa = A1[2 * D], rhob = B1[2 * D], Pa = A1[2 * D + 1], Pb = B1[2 * D + 1];
         const double omga = A1[2 * D + 3], omgb = B1[2 * D + 3];
@@ -918,9 +921,6 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_fac
             const double w2 = (PER && code != 0) ? cubic_spline(r2, p) : w1;
             const double ioa = 1. / omga, iob = 1. / omgb;
             const double psi1 = w1 * ioa, psi2 = w2 * iob;
-            double A2[PK2], B2[PK2]; // packed records: Binv, limited gradients (W order)
-            load_packed<PK2>(p.d.pk2 + (size_t)ia * PK2, A2);
-            load_packed<PK2>(p.d.pk2 + (size_t)ib * PK2, B2);
 #pragma unroll
             for (int al = 0; al < D; ++al) {
                 double t1 = 0., t2 = 0.;
