@@ -120,18 +120,21 @@ __global__ void __launch_bounds__(128) k_density_matrix(const Params p) {
     // omega: regular terms, then the self term, then the image terms.  (Keeping the kernel values of this sweep in
     // shared memory for the matrix sweep LOST, 0.100 -> 0.142 ms at 61^3: 32 KB per block is carved out of the L1 that
     // serves the neighbour gathers -- profiles/README.md r02a.)
-    // list entries are read two visits ahead and (2D) the next neighbour's coordinates prefetched into L1: each visit is
-    // an entry load followed by a dependent gather.  Measured r01t: KH 1M 0.546 -> 0.482 ms; in 3D the third prefetch per
-    // visit cost more than it hid (0.129 -> 0.133 ms), so only the entry pipeline is kept there.
+    // list entries are read two visits ahead, the next neighbour's coordinates one visit ahead (software pipeline: each
+    // visit is an entry load followed by a dependent gather)
     double omg = 0.;
     int e_next = nreg > 0 ? p.d.nnl[i] : 0, e_next2 = nreg > 1 ? p.d.nnl[(size_t)p.ncap + i] : 0;
+    double xn[3] = {0., 0., 0.}; // coordinates of the next neighbour, requested one visit ahead
+    if (nreg > 0) neighbour_position<D>(p, e_next, xn);
+#pragma unroll 2
     for (int s = 0; s < nreg; ++s) {
         double d[3], r;
         const int e = e_next;
+        const double xc[3] = {xn[0], xn[1], xn[2]};
         e_next = e_next2;
         if (s + 2 < nreg) e_next2 = p.d.nnl[(size_t)(s + 2) * p.ncap + i];
-        if (D == 2 && s + 1 < nreg) prefetch_position<D>(p, e_next & MLH_NNL_IDX_MASK);
-        neighbour_geometry<D, false>(p, xi, e, d, &r);
+        if (s + 1 < nreg) neighbour_position<D>(p, e_next, xn);
+        neighbour_geometry_from<D, false>(p, xi, e, xc, d, &r);
         omg = __dadd_rn(omg, cubic_spline(r, p));
     }
     omg = __dadd_rn(omg, cubic_spline(0., p));
@@ -167,13 +170,16 @@ __global__ void __launch_bounds__(128) k_density_matrix(const Params p) {
     for (int k = 0; k < D * D; ++k) E[k] = 0.;
     e_next = ntot > 0 ? p.d.nnl[i] : 0;
     e_next2 = ntot > 1 ? p.d.nnl[(size_t)p.ncap + i] : 0;
+    if (ntot > 0) neighbour_position<D>(p, e_next, xn);
+#pragma unroll 2
     for (int s = 0; s < ntot; ++s) {
         double d[3], r;
         const int e = e_next;
+        const double xc[3] = {xn[0], xn[1], xn[2]};
         e_next = e_next2;
         if (s + 2 < ntot) e_next2 = p.d.nnl[(size_t)(s + 2) * p.ncap + i];
-        if (D == 2 && s + 1 < ntot) prefetch_position<D>(p, e_next & MLH_NNL_IDX_MASK);
-        neighbour_geometry<D, PER>(p, xi, e, d, &r);
+        if (s + 1 < ntot) neighbour_position<D>(p, e_next, xn);
+        neighbour_geometry_from<D, PER>(p, xi, e, xc, d, &r);
         double psij = __ddiv_rn(cubic_spline(r, p), omg);
 #pragma unroll
         for (int a = 0; a < D; ++a)

@@ -233,21 +233,30 @@ __device__ __forceinline__ void neighbour_geometry(const Params &p, const double
     }
     *r = sqrt(dist_sqr_exact<D>(s));
 }
-// the displacement alone
-template <int D, bool PER>
-__device__ __forceinline__ void neighbour_delta(const Params &p, const double *xi, int e, double *d) {
+// the same in two halves, so that a caller can request the coordinates of the NEXT neighbour before it computes with
+// the current one (software pipeline of the gather)
+template <int D>
+__device__ __forceinline__ void neighbour_position(const Params &p, int e, double *xj) {
     const int j = e & MLH_NNL_IDX_MASK;
 #pragma unroll
+    for (int k = 0; k < D; ++k) xj[k] = p.d.x[k][j];
+}
+template <int D, bool PER>
+__device__ __forceinline__ void neighbour_geometry_from(const Params &p, const double *xi, int e, const double *xjraw, double *d,
+                                                        double *r) {
+    double s[3];
+#pragma unroll
     for (int k = 0; k < D; ++k) {
-        double xj = p.d.x[k][j];
+        double xj = xjraw[k];
         if (PER) {
             int ck = (e >> (MLH_NNL_IDX_BITS + 2 * k)) & 3;
             xj = image_coord(xj, ck, p.grid.bmin[k], p.grid.bmax[k]);
         }
         d[k] = __dsub_rn(xj, xi[k]);
+        s[k] = __dsub_rn(xi[k], xj);
     }
+    *r = sqrt(dist_sqr_exact<D>(s));
 }
-
 
 // Bounding box of Particles::getDomainLimits (Particles.cpp:228-267): per-thread running min / max (max already
 // excludes original particle 0, quirk Q8; NaN never passes `x < mn` / `x > mx`) -> warp shuffle -> shared memory ->
