@@ -27,9 +27,10 @@ def radial_profile(x, y, z, q, nbins=24, rmax=None):
     r = np.sqrt(x * x + y * y + z * z)
     rmax = float(r.max()) if rmax is None else rmax
     edges = np.linspace(0.0, rmax, nbins + 1)
-    which = np.clip(np.digitize(r, edges) - 1, 0, nbins - 1)
+    inside = r <= rmax  # the corners of a cubic box lie beyond the largest shell
+    which = np.clip(np.digitize(r[inside], edges) - 1, 0, nbins - 1)
     cnt = np.bincount(which, minlength=nbins)
-    tot = np.bincount(which, weights=q, minlength=nbins)
+    tot = np.bincount(which, weights=np.asarray(q)[inside], minlength=nbins)
     with np.errstate(invalid="ignore", divide="ignore"):
         mean = np.where(cnt > 0, tot / np.maximum(cnt, 1), np.nan)
     return 0.5 * (edges[1:] + edges[:-1]), mean, cnt
