@@ -200,21 +200,6 @@ __device__ __forceinline__ void store_packed(double *dst, const double *src) {
     for (int k = 0; k < N / 2; ++k) d2[k] = make_double2(src[2 * k], src[2 * k + 1]);
 }
 
-// L1 prefetch of the packed record of particle j (N doubles): issued a visit or two ahead of the gather that needs it
-template <int N>
-__device__ __forceinline__ void prefetch_record(const double *base, int j) {
-    const char *r = (const char *)(base + (size_t)j * N);
-#pragma unroll
-    for (int o = 0; o < N * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(r + o));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(r + N * 8 - 8));
-}
-
-template <int D>
-__device__ __forceinline__ void prefetch_position(const Params &p, int j) {
-#pragma unroll
-    for (int k = 0; k < D; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.d.x[k] + j));
-}
-
 // displacement (neighbour - self) and distance for list entry e of particle i, the way the reference
 // evaluates it for a regular neighbour (Particles.cpp:1170-1175) or a ghost (:2275-2280)
 template <int D, bool PER>
