@@ -1417,7 +1417,7 @@ int launch_chunks(mlh_ctx *c, double dt_fixed, double dt_max) {
     // blocks per SM of the streaming face kernels (setup / finish): tunable for A/B runs
     // persistent grids = two clean waves of the blocks each kernel keeps resident (register budgets pinned by
     // __launch_bounds__); sweeps: tools/grid_sweep.sh, profiles/README.md r01t / r01w / r01z
-    static const int g_setup = getenv("MLH_GRID_SETUP") ? atoi(getenv("MLH_GRID_SETUP")) : 16;
+    static const int g_setup = getenv("MLH_GRID_SETUP") ? atoi(getenv("MLH_GRID_SETUP")) : 24; // 3 waves of 8: 0.155 -> 0.152 / 1.335 -> 1.302 ms (r02h)
     static const int g_finish = getenv("MLH_GRID_FINISH") ? atoi(getenv("MLH_GRID_FINISH")) : 2 * MLH_FINISH_BLOCKS;
     // K4a: two clean waves of its resident blocks (3 per SM in 3D, 4 in 2D): 0.339 -> 0.309 ms at 61^3 (r01w)
     static const int g_states = getenv("MLH_GRID_STATES") ? atoi(getenv("MLH_GRID_STATES")) : 2 * MLH_K4A_BLOCKS_PER_SM(D);
