@@ -10,15 +10,17 @@
 
 class InitialDistribution {
 public:
+    /// reads the whole file; throws std::length_error when the datasets disagree in length
     InitialDistribution(const std::string &file);
     int getNumberOfParticles() const { return numberOfParticles; };
+    /// fills the host mirrors of `particles` (m, u, matId, x, y[, z], vx, vy[, vz]) and marks them for upload
     void getAllParticles(Particles &particles);
 
 private:
-    std::vector<double> m{}, u{};
-    std::vector<std::vector<double>> x{}, v{};
-    std::vector<int> matId{};
     int numberOfParticles{0};
+    std::vector<double> mass{}, energy{};                      // /m, /u          f64[N]
+    std::vector<std::vector<double>> position{}, velocity{};   // /x, /v          f64[N][>=DIM]
+    std::vector<int> material{};                               // /materialId     i8 | i32 [N]
 };
 
 #endif // MESHLESSHYDRO_INITIALDISTRIBUTION_H
