@@ -18,23 +18,26 @@
 // slab) or does not list the pair (one-sided periodic pair, quirk Q9) are owned by the listing side; two ranks then
 // evaluate a cut face redundantly with identical operands, so conservation holds across slabs without a flux exchange.
 //
-// Kernels (one thread per FACE in the first three):
-//   k_face_index      thread per particle: face list fa/fe (owner, list entry) + slot -> face map (fmap).
-//   k_face_states (K4a)  A_ij, boosted + reconstructed + limited + predicted states of both endpoints -> face
-//                        record (4D+4 doubles) in a field-major staging buffer.  Gather-bound; consecutive faces
-//                        share their owner, so half of the gather is a warp broadcast.
-//   k_face_riemann (K4b) rotate into the face frame, exact Riemann solve, rotate back, project -> F (D+2
-//                        doubles, canonical orientation) into the per-face flux array.  Pure FP64; the iteration
-//                        state lives in shared memory and unfinished faces are regrouped after every iteration.
+// Kernels:
+//   k_face_index      thread per particle, four list slots per trip: face list fa/fe (owner + canonical bit, list
+//                     entry) and the slot -> face map (fmap); a partner-owned slot is located in the partner's list
+//                     from the group start + bit mask K2 recorded (no search).
+//   k_face_states (K4a)  thread per face (persistent grid, two waves): A_ij, boosted + reconstructed + limited +
+//                        predicted states of both endpoints -> face record (4D+4 doubles) in a field-major staging
+//                        buffer.  Gather/latency-bound; consecutive faces share their owner (warp broadcast), the face
+//                        list is read one trip ahead and the next trip's records are prefetched into L1.
+//   k_face_setup / k_face_iterate / k_face_finish (K4b)  the Riemann class of the reference: rotate into the face
+//                        frame + start of the exact solver (faces that need iterations go to a queue) / persistent
+//                        lanes iterate queued faces to convergence (Newton-Raphson, Brent), state in registers, warp-
+//                        private cp.async rings / star state at x/t = 0, rotation back, projection -> F (D+2 doubles,
+//                        canonical orientation).  setup and finish stream at 60-80 % of the HBM peak, the iteration
+//                        is a dependent FP64 chain per lane.
 //                        [The first version fused everything into one 255-register, 145 KB kernel: ncu showed 56 %
 //                        of the warp stalls were instruction fetches and 14 % FP64-pipe use -- profiles/r01a_*.]
-//   k_flux_sum_update (K4c/K5) thread per particle: signed sum of the faces of its slots in list order,
-//                        conserved update, drift.
+//   k_flux_sum_update (K4c/K5) thread per particle, four slots per trip: signed sum of the faces of its slots in list
+//                        order, conserved update, drift, dt published, bounding box of the new positions reduced.
 // The per-slot buffers of the reference (psijTilde, Aij, WijL/R, Fij, vFrame for ALL particles, ~100 kB per
-// particle, Particles.h:201-229) are replaced by the chunk-sized staging buffer and 32/48 B of flux per face.
-//
-// Roofline: K4b is FP64-pipe bound; K4a/K4c are L2/HBM gather passes (staging traffic (4D+4)*8 B per face,
-// written once and read once).
+// particle, Particles.h:201-229) are replaced by the staging buffer and 32/48 B of flux per face.
 #include "mlh_internal.cuh"
 #include <cfloat>
 #include <cstdlib>
