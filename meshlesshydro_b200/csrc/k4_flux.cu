@@ -825,7 +825,7 @@ __device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4a: one thread per (slot, particle)
+// K4a: one thread per face
 // ---------------------------------------------------------------------------------------------
 // resident blocks per SM (register cap): 3D needs 168 registers to run spill-free (3 blocks: 0.360 -> 0.339 ms at 61^3),
 // 2D fits 128 and gains from the fourth block (KH 1M 0.86 ms vs 1.04 ms at 3) -- A/B r01v, profiles/README.md
