@@ -92,12 +92,15 @@ public:
     /// device -> host mirrors: state always; rho, P, rhoGrad, noi, cell when the step is past the gradient phase
     void syncHost();
     mlh_ctx *context() { return gpu; }
+    /// original indices of the particles slab `rank` of `nranks` owns (whole cell layers of the slowest axis; what the
+    /// multi-rank launcher uploads per rank) -- host arithmetic only
+    std::vector<int> slabParticles(int rank, int nranks);
     long kernelLaunches() const;
 
 private:
     enum Phase { PH_STATE = 0, PH_GRID = 1, PH_NEIGHBOURS = 2, PH_DENSITY = 3, PH_GRADIENTS = 4 };
     void ensure(int phase); // run the device phases up to `phase`
-    void selectShard();     // multi-rank runs: original indices of the particles in this rank's slab
+    void selectShard();     // multi-rank runs: shardIds = slabParticles(this rank)
     void check(int rc, const char *what);
     void checkFlags();
     void sums();

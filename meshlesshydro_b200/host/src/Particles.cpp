@@ -120,15 +120,15 @@ void Particles::configureDevice(const double &kernelSize, const double &gamma, c
     configured = true;
 }
 
-// The particles this rank owns: whole cell layers of the search grid along the slowest-varying axis (y in 2D, z in 3D:
+// The particles a rank owns: whole cell layers of the search grid along the slowest-varying axis (y in 2D, z in 3D:
 // cell id = iX + iY cellsX + iZ cellsX cellsY, Particles.cpp:298-302), the same split the device uses (mlh_slab_range).
 // Grid as Domain::createGrid builds it (Domain.cpp:9-54) from the periodic box or from getDomainLimits.
-void Particles::selectShard() {
+std::vector<int> Particles::slabParticles(int rank, int nranks) {
     double lim[2 * DIM];
 #if PERIODIC_BOUNDARIES
     for (int k = 0; k < 2 * DIM; ++k) lim[k] = boxCfg[k];
 #else
-    getDomainLimits(lim); // host loop: nothing is on the device yet
+    getDomainLimits(lim); // host loop while nothing is on the device yet
 #endif
     const int k = DIM - 1;
     const double *coord = y;
@@ -137,24 +137,27 @@ void Particles::selectShard() {
 #endif
     const double lo = lim[k], hi = lim[DIM + k];
     const int layers = (int)std::floor((hi - lo) / hCfg);
-    if (layers < 2 * mgpu::nranks()) {
-        Logger(ERROR) << "slab decomposition needs >= 2 cell layers per rank (" << layers << " layers, " << mgpu::nranks()
+    if (layers < 2 * nranks) {
+        Logger(ERROR) << "slab decomposition needs >= 2 cell layers per rank (" << layers << " layers, " << nranks
                       << " ranks) - Aborting.";
         die(21);
     }
     const double size = (hi - lo) / layers;
     int first = 0, last = 0;
-    if (mlh_slab_range(layers, mgpu::nranks(), mgpu::rank(), &first, &last) != MLH_OK) {
+    if (mlh_slab_range(layers, nranks, rank, &first, &last) != MLH_OK) {
         Logger(ERROR) << "mlh_slab_range failed - Aborting.";
         die(21);
     }
-    shardIds.clear();
+    std::vector<int> mine;
     for (int i = 0; i < N; ++i) {
         int layer = (int)std::floor((coord[i] - lo) / size);
         if (layer == layers) layer -= 1; // Particles.cpp:283-295
-        if (layer >= first && layer < last) shardIds.push_back(i);
+        if (layer >= first && layer < last) mine.push_back(i);
     }
+    return mine;
 }
+
+void Particles::selectShard() { shardIds = slabParticles(mgpu::rank(), mgpu::nranks()); }
 
 void Particles::ensure(int target) {
     if (ghostHolder) return;

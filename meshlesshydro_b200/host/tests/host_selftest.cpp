@@ -1,17 +1,39 @@
 // Host-only self test of the C++ mirror classes (no GPU needed): prints "key value" lines that
 // tests/test_host_cpu.py checks.  usage: host_selftest <config.info>
 #include <cstdio>
+#include <cstdlib>
+#include <string>
 #include <iostream>
 
 #include "../include/ConfigParser.h"
 #include "../include/Domain.h"
 #include "../include/Helper.h"
+#include "../include/InitialDistribution.h"
 #include "../include/Logger.h"
 #include "../include/Particles.h"
 
 structlog LOGCFG = {};
 
+// host_selftest shard <init.h5> <kernelSize> <nranks> [box limits...]: the slab decomposition of the multi-rank launcher
+static int shardMode(int argc, char **argv) {
+    InitialDistribution init{argv[2]};
+    Particles p{init.getNumberOfParticles()};
+    init.getAllParticles(p);
+    const double h = std::atof(argv[3]);
+    const int nranks = std::atoi(argv[4]);
+    double box[2 * DIM] = {0.};
+    for (int k = 0; k < 2 * DIM && 5 + k < argc; ++k) box[k] = std::atof(argv[5 + k]);
+    p.configureDevice(h, 5. / 3., box);
+    for (int r = 0; r < nranks; ++r) {
+        std::printf("shard%d", r);
+        for (int i : p.slabParticles(r, nranks)) std::printf(" %d", i);
+        std::printf("\n");
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc > 4 && std::string(argv[1]) == "shard") return shardMode(argc, argv);
     std::printf("DIM %d\n", DIM);
     if (argc > 1) {
         ConfigParser c{argv[1]};

@@ -200,3 +200,22 @@ def test_multi_rank_launcher_fails_loudly_without_gpus(tmp_path):
     assert "Slab decomposition over 2 GPUs" in r.stdout
     assert "mlh_create failed" in r.stdout
     assert os.listdir(tmp_path / "out") == []
+
+
+@pytest.mark.parametrize("case,nranks", [("kh2d", 2), ("kh2d", 3), ("sedov3d", 2), ("sedov3d", 4)])
+def test_cpp_launcher_shards_like_the_python_launcher(tmp_path, case, nranks):
+    """Particles::slabParticles (C++ multi-rank launcher) == multigpu.shard (bench / test launcher): same cell-layer
+    rule (Particles.cpp:279-302 on the slowest axis + mlh_slab_range), a partition of the particles."""
+    from meshlesshydro_b200 import h5lite, ic as IC, multigpu
+    ic = IC.kelvin_helmholtz(48, lattice=False) if case == "kh2d" else IC.sedov(24)
+    init = str(tmp_path / "init.h5")
+    h5lite.write_initial_conditions(init, ic)
+    args = ["shard", init, "%.17g" % ic["h"], str(nranks)] + (["%.17g" % v for v in ic["box"]] if ic.get("box") is not None else [])
+    r = _selftest(case, *args)
+    seen = []
+    for rank in range(nranks):
+        ids_cpp = np.array([int(v) for v in r["shard%d" % rank].split()], dtype=np.int64)
+        _, ids_py = multigpu.shard(ic, rank, nranks)
+        assert np.array_equal(ids_cpp, ids_py.astype(np.int64)), rank
+        seen.append(ids_cpp)
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(len(ic["x"])))
