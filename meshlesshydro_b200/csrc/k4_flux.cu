@@ -653,6 +653,10 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
     const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
     const int fs = p.d.face_start[i];
     bool over = false;
+    // the slot computed from group start + mask is re-checked against the partner's list only if some list of this step
+    // was cut at max_interactions (flag raised by K2, earlier on this stream): otherwise the relation is symmetric and
+    // the check would be one more gather per slot for nothing
+    const bool verify = (*p.d.flags & MLH_F_MAX_INTERACTIONS) != 0u;
     // Four slots per trip: a partner-owned slot is a chain of dependent gathers (entry -> j's group start, mask and list
     // length -> j's slot -> its face), latency-bound one at a time; the four chains of a trip are independent.
     for (int s0 = 0; s0 < ntot; s0 += 4) {
@@ -693,7 +697,7 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
                 if (tt < nrj[q]) {
                     t[q] = tt;
                     vj[q] = p.d.fmap[(size_t)tt * p.ncap + j]; // owned by j: rank << 2 | 2 | sign
-                    if (p.d.nnl[(size_t)tt * p.ncap + j] != i) t[q] = -1; // j's list was cut at max_interactions
+                    if (verify && p.d.nnl[(size_t)tt * p.ncap + j] != i) t[q] = -1; // j's list was cut at max_interactions
                 }
             }
         }
