@@ -168,6 +168,11 @@ int mlh_grid_info(mlh_ctx *ctx, int *cells3, double *cell_size3, double *bounds6
  * neighbour lists: "nnl"/"nnlGhosts" -> int[N*max_interactions], row i = ORIGINAL ids of the
  *          regular neighbours (resp. parent ids of the ghost neighbours) of particle i in list
  *          order; "nnlGhostCodes" the image code of each ghost entry (2 bits/dim: 1=+L, 2=-L).
+ * per face (debug_capture, after mlh_advance/mlh_step; single GPU): "face_pairs" -> int[3*F]: original ids of the
+ *          canonical endpoint a (the lower id, which solves the face in the reference, Particles.cpp:1841,1889) and of
+ *          its partner b, and the image code of b in a's list; "face_rec" -> double[F*(4*DIM+4)]: the reference's
+ *          per-slot WijR[a-slot] (state of a), WijL (state of b), vFrame, Aij (Particles.cpp:1290-1311,1488-1733);
+ *          "face_F" -> double[F*(DIM+2)]: Fij of that slot (Particles.cpp:1787-1911).
  * Returns the element count written, or <0.  dst NULL -> just the count.
  */
 long mlh_debug_fetch(mlh_ctx *ctx, const char *field, void *dst, long dst_elems);

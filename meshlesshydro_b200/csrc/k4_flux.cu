@@ -1072,6 +1072,19 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_fac
         }
         if (PER && code != 0 && (Wa[1] < 0. || Wb[1] < 0.)) atomicOr(p.d.flags, MLH_F_NEG_GHOST_PRESSURE);
 
+        if (p.debug_capture) { // parity harness: the reference's per-slot WijR / WijL / vFrame / Aij of this face (mlh_debug_fetch "face_rec")
+            double *dbg = p.d.dbg_face + (size_t)f * R::NREC;
+#pragma unroll
+            for (int nu = 0; nu < NW; ++nu) {
+                dbg[R::WA + nu] = Wa[nu];
+                dbg[R::WB + nu] = Wb[nu];
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                dbg[R::VF + k] = vF[k];
+                dbg[R::AA + k] = A[k];
+            }
+        }
         // ---- stage the record (field-major inside the chunk: coalesced here and in K4b) ----
         double *rec = stage + (f - f0);
         const size_t fs = (size_t)cstride; // field stride

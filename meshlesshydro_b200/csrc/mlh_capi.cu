@@ -101,6 +101,7 @@ static void carve_pool(mlh_ctx *c, Carver &cv) {
             for (int a = 0; a < D; ++a) d.gpre[f * 3 + a] = cv.take<double>(n);
         }
         for (int k = 0; k < 2 + D; ++k) d.flux[k] = cv.take<double>(n);
+        d.dbg_face = cv.take<double>((size_t)p.fcap * (4 * D + 4));
     }
     d.dt_bits = cv.take<unsigned long long>(1);
     d.dt_used = cv.take<double>(1);
@@ -280,6 +281,10 @@ int mlh_create(const mlh_config *cfg, mlh_ctx **out) {
         snprintf(g_create_err, sizeof(g_create_err), "dim must be 2 or 3 (got %d)", cfg->dim);
         return MLH_E_INVALID;
     }
+    if (cfg->max_interactions > 1023) { // the slot -> face map packs a per-particle rank into 10 bits
+        snprintf(g_create_err, sizeof(g_create_err), "max_interactions must be <= 1023 (got %d)", cfg->max_interactions);
+        return MLH_E_INVALID;
+    }
     if (!(cfg->kernel_size > 0.) || !(cfg->gamma > 1.)) {
         snprintf(g_create_err, sizeof(g_create_err), "kernel_size must be > 0 and gamma > 1");
         return MLH_E_INVALID;
@@ -415,6 +420,18 @@ int mlh_upload(mlh_ctx *c, long N, const double *x, const double *y, const doubl
     if (N <= 0 || N > MLH_NNL_IDX_MASK || !x || !y || !vx || !vy || !m || !u || (p.D == 3 && (!z || !vz))) {
         snprintf(c->err, sizeof(c->err), "mlh_upload: bad arguments (N=%ld, need 0 < N < 2^26, z/vz required in 3D)", N);
         return MLH_E_INVALID;
+    }
+    if (c->cfg.nranks == 1 && global_ids) {
+        // the download / parity paths scatter by id into N-element buffers: ids must be a permutation of 0..N-1
+        std::vector<unsigned char> seen((size_t)N, 0);
+        for (long i = 0; i < N; ++i) {
+            const int id = global_ids[i];
+            if (id < 0 || id >= N || seen[(size_t)id]) {
+                snprintf(c->err, sizeof(c->err), "mlh_upload: global_ids must be a permutation of 0..N-1 on a single GPU (entry %ld = %d)", i, id);
+                return MLH_E_INVALID;
+            }
+            seen[(size_t)id] = 1;
+        }
     }
     long cap = c->cfg.capacity > 0 ? c->cfg.capacity : (c->cfg.nranks > 1 ? N + N / 2 + 4096 : N);
     if (cap < N) cap = N;
@@ -869,6 +886,24 @@ __global__ void k_export_lists(const Params p, int which, int *out, int n_rows) 
         out[(size_t)row * p.max_ni + s] = val;
     }
 }
+// per face: ORIGINAL ids of the canonical endpoint a (lower id: the one that solves the face in the reference,
+// Particles.cpp:1841,1889) and of its partner b, and the periodic-image code of b as a lists it
+__global__ void k_export_face_pairs(const Params p, int nfaces, int *out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfaces) return;
+    const int fav = p.d.fa[f], e = p.d.fe[f];
+    const int i = fav & 0x7FFFFFFF, j = e & MLH_NNL_IDX_MASK;
+    const int code = (int)((unsigned)e >> MLH_NNL_IDX_BITS);
+    const bool canon = fav >= 0;
+    out[3 * f + 0] = p.d.id[canon ? i : j];
+    out[3 * f + 1] = p.d.id[canon ? j : i];
+    out[3 * f + 2] = canon ? code : reverse_code(code);
+}
+__global__ void k_export_face_flux(const Params p, int nfaces, double *out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfaces) return;
+    for (int nu = 0; nu < p.D + 2; ++nu) out[(size_t)f * (p.D + 2) + nu] = p.d.F[(size_t)f * MLH_FREC(p.D) + nu];
+}
 __global__ void k_iota_sorted_index(const Params p, int *out) {
     int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.own_end) return;
@@ -998,6 +1033,37 @@ extern "C" long mlh_debug_fetch(mlh_ctx *c, const char *field, void *dst, long d
         if (cudaMalloc(&tmp, sizeof(int) * (size_t)count) != cudaSuccess) return MLH_E_CUDA;
         k_export_lists<<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p, which, tmp, n);
         cudaMemcpyAsync(dst, tmp, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(tmp);
+        return count;
+    }
+    if (f == "face_pairs" || f == "face_rec" || f == "face_F") { // per-face intermediates (a16/a17/a19): single GPU
+        int nf = 0;
+        cudaMemcpyAsync(&nf, p.d.face_start + p.own_end, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        if (nf > p.fcap) nf = p.fcap;
+        const int per = f == "face_pairs" ? 3 : (f == "face_rec" ? 4 * D + 4 : D + 2);
+        const long count = (long)nf * per;
+        if (!dst) return count;
+        if (dst_elems < count) return MLH_E_INVALID;
+        if (f == "face_rec") {
+            if (!p.debug_capture || c->phase != 0) {
+                snprintf(c->err, sizeof(c->err), "mlh_debug_fetch(face_rec): needs debug_capture and a completed flux pass");
+                return MLH_E_STATE;
+            }
+            cudaMemcpyAsync(dst, p.d.dbg_face, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, c->stream);
+            cudaStreamSynchronize(c->stream);
+            return count;
+        }
+        void *tmp = nullptr;
+        const size_t bytes = (size_t)count * (f == "face_pairs" ? sizeof(int) : sizeof(double));
+        if (count == 0) return 0;
+        if (cudaMalloc(&tmp, bytes) != cudaSuccess) return MLH_E_CUDA;
+        if (f == "face_pairs")
+            k_export_face_pairs<<<mlh_blocks(nf, 256), 256, 0, c->stream>>>(p, nf, (int *)tmp);
+        else
+            k_export_face_flux<<<mlh_blocks(nf, 256), 256, 0, c->stream>>>(p, nf, (double *)tmp);
+        cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, c->stream);
         cudaStreamSynchronize(c->stream);
         cudaFree(tmp);
         return count;

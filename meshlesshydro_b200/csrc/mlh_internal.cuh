@@ -76,6 +76,7 @@ struct DevPtrs {
     // debug capture (may be null)
     double *gpre[15];
     double *flux[5]; // mF, eF, vF[3]
+    double *dbg_face; // debug_capture: per face (AoS, 4D+4 doubles) WijR (canonical endpoint), WijL, vFrame, Aij as K4a formed them
     // reductions
     unsigned long long *dt_bits; // min CFL dt as ordered bit pattern
     double *bbox;                // [0..2] min, [3..5] max over i>=1 (quirk Q8) as ORDERED KEYS (dbl_key), [6..8] x[0] as doubles

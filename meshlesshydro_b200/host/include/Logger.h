@@ -34,7 +34,9 @@ public:
     }
 
 private:
-    bool enabled() const { return msglevel >= LOGCFG.level && (LOGCFG.outputRank == -1 || LOGCFG.myRank == LOGCFG.outputRank); }
+    bool enabled() const {
+        return msglevel >= LOGCFG.level && (msglevel >= ERROR || LOGCFG.outputRank == -1 || LOGCFG.myRank == LOGCFG.outputRank);
+    }
     std::ostringstream line; // the whole line is emitted at once (ranks do not interleave inside a line)
     bool opened = false;
     typelog msglevel = DEBUG;

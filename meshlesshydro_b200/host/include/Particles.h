@@ -111,6 +111,8 @@ private:
     int phase{PH_STATE};
     double sumCache[6];
     bool sumsValid{false};
+    int listCapacity{0};          // neighbour-list capacity the device context was created with (for the exit(1) message)
+    bool flagsCheckedOnce{false}; // device flags read after the first neighbour search (reference: exit inside gridNNS)
     double hCfg{0.}, gammaCfg{0.};
     double boxCfg[2 * DIM];
     bool configured{false};

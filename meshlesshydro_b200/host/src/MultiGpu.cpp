@@ -49,9 +49,9 @@ void launch() {
     pthread_barrierattr_t attr;
     pthread_barrierattr_init(&attr);
     pthread_barrierattr_setpshared(&attr, PTHREAD_PROCESS_SHARED);
-    pthread_barrier_init(&g_ctl->barrier, &attr, (unsigned)g_planned);
+    g_nranks = g_planned > 64 ? 64 : g_planned; // the barrier counts the ranks that really exist
+    pthread_barrier_init(&g_ctl->barrier, &attr, (unsigned)g_nranks);
     pthread_barrierattr_destroy(&attr);
-    g_nranks = g_planned > 64 ? 64 : g_planned;
     g_ctl->pids[0] = getpid();
     std::fflush(stdout);
     std::fflush(stderr);

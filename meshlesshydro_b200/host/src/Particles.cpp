@@ -95,9 +95,17 @@ void Particles::check(int rc, const char *what) {
 void Particles::checkFlags() {
     const unsigned f = mlh_error_flags(gpu);
     if (f & MLH_F_MAX_INTERACTIONS) {
-        Logger(ERROR) << "MAX_NUM_INTERACTIONS exceeded for at least one particle (device list capacity "
-                      << envInt("MLH_MAX_INTERACTIONS", 0) << ", 0 = default) - Aborting."; // Particles.cpp:348-352 / :2249-2253
+        Logger(ERROR) << "MAX_NUM_INTERACTIONS exceeded for at least one particle (device list capacity " << listCapacity
+                      << ", set MLH_MAX_INTERACTIONS to change it) - Aborting."; // Particles.cpp:348-352 / :2249-2253
         die(1);
+    }
+    if (f & (MLH_F_MIGRATION | MLH_F_HALO_OVERFLOW)) {
+        // a particle that crossed more than one cell layer of a slab in one step is no longer owned by any rank, a halo
+        // buffer that overflowed dropped particles: mass and energy would change silently
+        Logger(ERROR) << ((f & MLH_F_MIGRATION) ? "A particle moved across more than one cell layer of its slab in one step"
+                                                : "Halo / migration buffer overflow")
+                      << " (multi-GPU run; raise the capacity or lower the time step) - Aborting.";
+        die(23);
     }
     if (f & MLH_F_OUT_OF_GRID) {
         Logger(ERROR) << "Particle outside of the search grid. - Aborting.";
@@ -171,9 +179,12 @@ void Particles::ensure(int target) {
         cfg.dim = DIM;
         cfg.periodic = PERIODIC_BOUNDARIES;
         // list capacity: the reference reserves MAX_NUM_INTERACTIONS (+ MAX_NUM_GHOST_INTERACTIONS) slots per particle
-        // (~100 kB per particle); the device lists are sized by MLH_MAX_INTERACTIONS (default min(that, 192))
+        // (~100 kB per particle); the device lists hold 16 B per slot and default to the same capacity (MLH_MAX_INTERACTIONS
+        // lowers it for large runs)
         int cap = MAX_NUM_INTERACTIONS + (PERIODIC_BOUNDARIES ? MAX_NUM_GHOST_INTERACTIONS : 0);
-        cfg.max_interactions = envInt("MLH_MAX_INTERACTIONS", cap < 192 ? cap : 192);
+        if (cap > 1023) cap = 1023; // limit of the device's slot -> face map
+        cfg.max_interactions = envInt("MLH_MAX_INTERACTIONS", cap);
+        listCapacity = cfg.max_interactions;
         cfg.slope_limiting = SLOPE_LIMITING;
         cfg.pairwise_limiter = PAIRWISE_LIMITER;
         cfg.meshless_finite_mass = MESHLESS_FINITE_MASS;
@@ -254,6 +265,13 @@ void Particles::ensure(int target) {
     if (phase < PH_NEIGHBOURS && target >= PH_NEIGHBOURS) {
         check(mlh_neighbours(gpu), "mlh_neighbours");
         phase = PH_NEIGHBOURS;
+        // the reference exits inside gridNNS / ghostNNS (Particles.cpp:348-352, :2249-2253), i.e. before anything is
+        // computed or dumped from a truncated list.  Reading the flag word synchronises, so it is done every step only
+        // when MLH_CHECK_EVERY_STEP is set, otherwise on the first step and then after each update.
+        if (!flagsCheckedOnce || envInt("MLH_CHECK_EVERY_STEP", 0)) {
+            checkFlags();
+            flagsCheckedOnce = true;
+        }
     }
     if (phase < PH_DENSITY && target >= PH_DENSITY) {
         check(mlh_density_matrix(gpu), "mlh_density_matrix");

@@ -103,7 +103,10 @@ int main(int argc, char *argv[]) {
     if (mgpu::planned() > 1) {
         Logger(INFO) << "    > Slab decomposition over " << mgpu::planned() << " GPUs (one process each)";
         mgpu::launch(); // no CUDA call so far; the parent continues as rank 0
-        if (mgpu::rank() != 0) LOGCFG.level = ERROR;
+        // every rank keeps the SAME verbosity level: it decides which collective sanity sums the time loop evaluates
+        // (MeshlessScheme::densityAndPressure), so it must not differ between ranks; only rank 0 prints (errors: all)
+        LOGCFG.myRank = mgpu::rank();
+        LOGCFG.outputRank = 0;
     }
     Logger(INFO) << "... done. Initializing simulation ...";
 

@@ -88,6 +88,14 @@ class _Base:
     def step(self, dt_fixed=-1.0, dt_max=-1.0, stop_after=0):
         return self._step(self.ctx, dt_fixed, dt_max, stop_after)
 
+    @property
+    def max_ni(self):  # slots per particle of the per-slot arrays (MAX_NUM_INTERACTIONS)
+        return self.cfg.max_ni if hasattr(self, "cfg") else self.info["max_ni"]
+
+    @property
+    def max_gi(self):  # MAX_NUM_GHOST_INTERACTIONS
+        return self.cfg.max_gi if hasattr(self, "cfg") else self.info["max_gi"]
+
     def fetch(self, name):
         n = self._fetch(self.ctx, name.encode(), None)
         if n < 0:

@@ -4,25 +4,50 @@ import numpy as np
 from meshlesshydro_b200 import capi, ic as IC
 from cpu_oracles import Oracle, make_config as orc_config
 
-# Floating-point tolerance of north_star: <= 1e-10 relative per particle.  "Relative" is taken
-# against |reference value| + the field's scale (max |reference| over all particles): a pure
-# per-value relative error is undefined where a gradient or a flux sum cancels to ~0.
+# Floating-point tolerance of north_star: <= 1e-10 relative error PER PARTICLE.
+#   * strictly positive per-particle quantities (x, y, z, m, u, rho, P, omega) are compared with the plain relative
+#     error |gpu - ref| / |ref| of every single particle (`close_rel`).  The only concession: a value more than 14
+#     decades below the field's maximum (round-off of a quantity that is analytically zero, e.g. a coordinate that
+#     is exactly 0 on a lattice) is measured against that floor instead of against itself;
+#   * quantities that are sums of cancelling terms (velocities of a fluid at rest, gradients, flux sums) have no
+#     meaningful per-value relative error where they cancel to ~0; they are measured against |ref| + the field's
+#     scale (max |ref| over all particles) (`close`).
 RTOL = 1e-10
+STRICT = ("x", "y", "z", "m", "u", "rho", "P", "omega")
 
 
-def close(a, b, rtol=RTOL, what=""):
+def _finite_pair(a, b, what):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, (what, a.shape, b.shape)
     nan_a, nan_b = np.isnan(a), np.isnan(b)
     assert np.array_equal(nan_a, nan_b), "%s: NaN pattern differs (%d vs %d)" % (what, nan_a.sum(), nan_b.sum())
     fin = ~nan_a
-    if not fin.any():
+    return a[fin], b[fin]
+
+
+def close(a, b, rtol=RTOL, what=""):
+    """scaled rule: |a - b| / (|b| + max|b|) -- for cancelling quantities only"""
+    a, b = _finite_pair(a, b, what)
+    if a.size == 0:
         return 0.0
-    scale = np.max(np.abs(b[fin]))
-    err = np.abs(a[fin] - b[fin]) / (np.abs(b[fin]) + scale + 1e-300)
+    scale = np.max(np.abs(b))
+    err = np.abs(a - b) / (np.abs(b) + scale + 1e-300)
     worst = float(err.max())
     assert worst <= rtol, "%s: max scaled error %.3e > %.1e" % (what, worst, rtol)
+    return worst
+
+
+def close_rel(a, b, rtol=RTOL, what=""):
+    """plain per-particle relative error |a - b| / |b| (floor: 1e-14 of the field's maximum)"""
+    a, b = _finite_pair(a, b, what)
+    if a.size == 0:
+        return 0.0
+    floor = 1e-14 * np.max(np.abs(b)) + 1e-300
+    err = np.abs(a - b) / np.maximum(np.abs(b), floor)
+    worst = float(err.max())
+    assert worst <= rtol, "%s: max per-particle relative error %.3e > %.1e (particle %d: %r vs %r)" % (
+        what, worst, rtol, int(err.argmax()), a[err.argmax()], b[err.argmax()])
     return worst
 
 
@@ -64,7 +89,7 @@ def compare_prepare(ic, orc, gpu):
     assert np.array_equal(gpu.fetch("cell"), orc.fetch("cell")), "cell assignment differs"
     noi_g, noi_o = gpu.fetch("noi"), orc.fetch("noi")
     assert np.array_equal(noi_g, noi_o), "noi differs at %d particles" % int((noi_g != noi_o).sum())
-    cap_g, cap_o = gpu.cfg.max_interactions, orc.cfg.max_ni
+    cap_g, cap_o = gpu.cfg.max_interactions, orc.max_ni
     rows_g = gpu.fetch("nnl").reshape(N, cap_g)
     rows_o = orc.fetch("nnl").reshape(N, cap_o)
     W = min(cap_g, cap_o)
@@ -75,15 +100,18 @@ def compare_prepare(ic, orc, gpu):
         ng_g, ng_o = gpu.fetch("noiGhosts"), orc.fetch("noiGhosts")
         assert np.array_equal(ng_g, ng_o), "noiGhosts differs at %d particles" % int((ng_g != ng_o).sum())
         parent = orc.fetch("ghost_parent")
-        gl_o = orc.fetch("nnlGhosts").reshape(N, orc.cfg.max_gi)
+        gl_o = orc.fetch("nnlGhosts").reshape(N, orc.max_gi)
         gl_g = gpu.fetch("nnlGhosts").reshape(N, cap_g)
         for i in np.nonzero(ng_o)[0]:
             assert np.array_equal(parent[gl_o[i, :ng_o[i]]], gl_g[i, :ng_o[i]]), "ghost list of particle %d differs" % i
     # --- floating point ---
     worst = {}
     for name in ("omega", "rho", "P"):
-        worst[name] = close(gpu.fetch(name), orc.fetch(name), what=name)
-    worst["Binv"] = close(gpu.fetch("Binv"), orc.fetch("Binv"), what="Binv")
+        worst[name] = close_rel(gpu.fetch(name), orc.fetch(name), what=name)
+    try:
+        worst["Binv"] = close(gpu.fetch("Binv"), orc.fetch("Binv"), what="Binv")
+    except KeyError:
+        pass  # the reference-source build keeps only the psi-tilde weights, not the matrix
     worst["gradPre"] = close(gpu.fetch("gradPre"), orc.fetch("gradPre"), what="gradPre")
     names = ["rhoGrad", "vxGrad", "vyGrad", "PGrad"] + (["vzGrad"] if D == 3 else [])
     for name in names:
@@ -97,5 +125,98 @@ def compare_state(ic, orc, gpu, rtol=RTOL, skip=None):
     worst = {}
     keep = slice(None) if skip is None else ~skip
     for name in ["x", "y", "vx", "vy", "m", "u"] + (["z", "vz"] if D == 3 else []):
-        worst[name] = close(st[name][keep], orc.fetch(name)[keep], rtol=rtol, what=name)
+        cmp = close_rel if name in STRICT else close
+        worst[name] = cmp(st[name][keep], orc.fetch(name)[keep], rtol=rtol, what=name)
+    return worst
+
+
+def compare_faces(ic, orc, gpu, rtol=RTOL, fields=("Aij", "WijR", "WijL", "vFrame", "Fij")):
+    """Per-face intermediates after a full step on both sides: the GPU's unique faces against the reference's per-slot
+    arrays at the slot of the canonical (lower-index) endpoint -- Aij (Particles.cpp:1290-1311), WijR/WijL/vFrame
+    (:1488-1733) and Fij (:1787-1911); periodic-image faces against the *Ghosts arrays (:2504-2683, :1862-1907).
+    Faces of one-sided seam pairs (quirk Q9: the reference reads stale memory there) are skipped and counted.
+    Error measures: A against the face's |A|; rho, P strictly relative; velocities against |v| + the face's sound
+    speed; F against the largest flux component of the face."""
+    D, N = ic["dim"], len(ic["x"])
+    NW = D + 2
+    pairs = gpu.fetch("face_pairs").reshape(-1, 3).astype(np.int64)
+    rec = gpu.fetch("face_rec").reshape(-1, 4 * D + 4)
+    Fg = gpu.fetch("face_F").reshape(-1, NW)
+    nf = len(pairs)
+    assert nf == int(gpu.fetch("num_faces")[0]) and nf > 0
+    a, b, code = pairs[:, 0], pairs[:, 1], pairs[:, 2]
+    assert np.all(a < b), "canonical endpoint must be the lower original index (quirk Q4)"
+    M = orc.max_ni
+    noi = orc.fetch("noi").astype(np.int64)
+    nnl = orc.fetch("nnl").reshape(N, M).astype(np.int64)
+    smask = np.arange(M)[None, :] < noi[:, None]
+    rows = np.broadcast_to(np.arange(N, dtype=np.int64)[:, None], (N, M))[smask]
+    keys = rows * N + nnl[smask]
+    flat = (rows * M + np.broadcast_to(np.arange(M, dtype=np.int64)[None, :], (N, M))[smask])
+    order = np.argsort(keys, kind="stable")
+    keys, flat = keys[order], flat[order]
+    reg = code == 0
+    want = a[reg] * N + b[reg]
+    pos = np.searchsorted(keys, want)
+    assert np.all(pos < len(keys)) and np.array_equal(keys[np.minimum(pos, len(keys) - 1)], want), \
+        "a regular face is missing from the reference's list of its canonical endpoint"
+    slot_reg = flat[pos]
+    sel = {"reg": (np.nonzero(reg)[0], slot_reg, "")}
+    skipped = 0
+    if ic["periodic"] and (~reg).any():
+        MG = orc.max_gi
+        parent = orc.fetch("ghost_parent").astype(np.int64)
+        nog = orc.fetch("noiGhosts").astype(np.int64)
+        gl = orc.fetch("nnlGhosts").reshape(N, MG).astype(np.int64)
+        gmask = np.arange(MG)[None, :] < nog[:, None]
+        grow = np.broadcast_to(np.arange(N, dtype=np.int64)[:, None], (N, MG))[gmask]
+        gkeys = grow * N + parent[gl[gmask]]
+        gflat = grow * MG + np.broadcast_to(np.arange(MG, dtype=np.int64)[None, :], (N, MG))[gmask]
+        o2 = np.argsort(gkeys, kind="stable")
+        gkeys, gflat = gkeys[o2], gflat[o2]
+        gi = np.nonzero(~reg)[0]
+        gwant = a[gi] * N + b[gi]
+        gpos = np.minimum(np.searchsorted(gkeys, gwant), len(gkeys) - 1)
+        found = gkeys[gpos] == gwant
+        skipped = int((~found).sum())
+        sel["ghost"] = (gi[found], gflat[gpos[found]], "Ghosts")
+    Wa, Wb, vF, A = rec[:, :NW], rec[:, NW:2 * NW], rec[:, 2 * NW:2 * NW + D], rec[:, 2 * NW + D:]
+    worst = {}
+
+    def upd(name, err):
+        # entries where either side is non-finite (quirk Q13 can make the reference itself produce inf/NaN states) come
+        # out as NaN: there both sides must show the same pattern, which the flux sums / state comparisons check
+        if err.size:
+            err = np.where(np.isnan(err), 0.0, err)
+            worst[name] = max(worst.get(name, 0.0), float(err.max()))
+
+    for kind, (fidx, slots, suffix) in sel.items():
+        if fidx.size == 0:
+            continue
+        for name in fields:
+            if name == "vFrame" and suffix:
+                continue  # the ghost overload keeps no separate frame-velocity array in the fetch list
+            width = D if name in ("Aij", "vFrame") else NW
+            ref = orc.fetch(name + suffix).reshape(-1, width)[slots]
+            if name == "Aij":
+                g = A[fidx]
+                upd(name, np.abs(g - ref).max(axis=1) / (np.sqrt((ref * ref).sum(axis=1)) + 1e-300))
+            elif name == "vFrame":
+                g = vF[fidx]
+                cs = np.sqrt(ic["gamma"] * Wa[fidx, 1] / Wa[fidx, 0])
+                upd(name, np.abs(g - ref).max(axis=1) / (np.abs(ref).max(axis=1) + cs))
+            elif name in ("WijR", "WijL"):
+                g = (Wa if name == "WijR" else Wb)[fidx]
+                upd(name + ".rho", np.abs(g[:, 0] - ref[:, 0]) / np.abs(ref[:, 0]))
+                upd(name + ".P", np.abs(g[:, 1] - ref[:, 1]) / np.abs(ref[:, 1]))
+                cs = np.sqrt(ic["gamma"] * np.abs(ref[:, 1] / ref[:, 0]))
+                upd(name + ".v", np.abs(g[:, 2:] - ref[:, 2:]).max(axis=1) / (np.abs(ref[:, 2:]).max(axis=1) + cs))
+            else:
+                g = Fg[fidx]
+                upd(name, np.abs(g - ref).max(axis=1) / (np.abs(ref).max(axis=1) + 1e-300))
+            del ref
+    bad = {k: v for k, v in worst.items() if not (v <= rtol)}
+    assert not bad, "per-face intermediates off: %r (tolerance %.1e)" % (bad, rtol)
+    worst["faces"] = nf
+    worst["skipped_one_sided"] = skipped
     return worst

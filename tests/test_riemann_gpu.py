@@ -73,3 +73,63 @@ def test_inputs_untouched_and_antisymmetry():
     scale = np.abs(F).max(axis=1, keepdims=True) + 1e-300
     assert (np.abs(F + G) / scale).max() <= 1e-9
     gpu.close()
+
+
+def _vacuum_faces(dim, n, seed):
+    """Faces whose Riemann problem contains or generates vacuum (Toro 4.6; Riemann.cpp:104-127: the solver returns
+    flag 0 when the sampled point lies in the vacuum region): right state vacuum, left state vacuum, both vacuum,
+    and strongly receding flows with 2/(g-1) (a_L + a_R) <= u_R - u_L, sampled on either side of and inside the gap."""
+    rng = np.random.default_rng(seed)
+    nw = dim + 2
+    WL = np.empty((n, nw))
+    WR = np.empty((n, nw))
+    for W in (WL, WR):
+        W[:, 0] = rng.uniform(0.5, 2.0, n)
+        W[:, 1] = rng.uniform(0.5, 2.0, n)
+        W[:, 2:] = rng.normal(0, 0.2, (n, dim))
+    kind = np.arange(n) % 6
+    WR[kind == 0, 0] = 0.0                      # right vacuum
+    WR[kind == 0, 1] = 0.0
+    WL[kind == 1, 0] = 0.0                      # left vacuum
+    WL[kind == 1, 1] = 0.0
+    both = kind == 2
+    WL[both, :2] = 0.0
+    WR[both, :2] = 0.0
+    gen = kind >= 3                             # generated vacuum: receding faster than both fans can follow
+    A = np.zeros((n, dim))
+    A[:, 0] = rng.uniform(0.01, 1.0, n)         # faces along +x: the normal velocity is component 0
+    A[:, 1:] = rng.normal(0, 0.05, (n, dim - 1))
+    pull = rng.uniform(12.0, 16.0, n)
+    WL[gen, 2] -= pull[gen]
+    WR[gen, 2] += pull[gen]
+    shift = np.where(kind == 4, 9.0, np.where(kind == 5, -9.0, 0.0))  # move the gap off x/t = 0: fans get sampled
+    WL[:, 2] += shift
+    WR[:, 2] += shift
+    vF = rng.normal(0, 0.3, (n, dim))
+    return WR, WL, vF, A
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_vacuum_faces_match_oracle_and_raise_the_flag(dim):
+    """The vacuum sampler of the device solver (rs_solve_vacuum, MLH_PSTAR_VACUUM path of k_face_finish) against the
+    oracle, and MLH_F_VACUUM = the reference's "Vacuum state sampled" (Riemann.cpp:113,126)."""
+    from meshlesshydro_b200 import ic as IC
+    gamma = 5.0 / 3.0
+    WR, WL, vF, A = _vacuum_faces(dim, 1200, seed=40 + dim)
+    preset = "fb2d" if dim == 2 else "sedov3d"
+    gpu = capi.MfvGpu(capi.make_config(preset, 0.2, gamma))
+    gpu.upload(IC.fluid_block(8) if dim == 2 else IC.sedov(4))  # gives the context its device flag word
+    assert gpu.error_flags() == 0
+    F = gpu.riemann_faces(WR, WL, vF, A)
+    ref = _oracle_fluxes(dim, 0, gamma, WR, WL, vF, A)
+    assert np.array_equal(np.isnan(F), np.isnan(ref))
+    fin = ~np.isnan(ref).any(axis=1)
+    scale = np.abs(ref[fin]).max(axis=1, keepdims=True)
+    err = np.abs(F[fin] - ref[fin]) / np.where(scale > 0, scale, 1.0)
+    assert err.max() <= 1e-10, (err.max(), np.unravel_index(err.argmax(), err.shape))
+    # faces that sample the vacuum itself carry no mass and no energy
+    kind = np.arange(len(WR)) % 6
+    assert np.all(F[kind == 2][:, 0] == 0.0) and np.mean(F[kind == 3][:, 0] == 0.0) > 0.9
+    assert np.array_equal(F[:, 0] == 0.0, ref[:, 0] == 0.0), "the set of faces that sample the vacuum differs" 
+    assert gpu.error_flags() & capi.F_VACUUM
+    gpu.close()

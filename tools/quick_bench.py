@@ -31,6 +31,8 @@ for w in which:
     if w == "kh1000": run(w, IC.kelvin_helmholtz(1000), "kh2d")
     if w == "kh1000j": run(w, IC.kelvin_helmholtz(1000, lattice=True, jitter=0.2), "kh2d", max_interactions=96)
     if w == "kh2000": run(w, IC.kelvin_helmholtz(2000), "kh2d", steps=3)
+    if w == "kh2000j": run(w, IC.kelvin_helmholtz(2000, lattice=True, jitter=0.2), "kh2d", steps=3, max_interactions=96)
+    if w == "fb1000j": run(w, IC.fluid_block(1000, jitter=0.05), "fb2d", max_interactions=96)
     if w == "sedov31": run(w, IC.sedov(31), "sedov3d")
     if w == "sedov61": run(w, IC.sedov(61), "sedov3d", abs_mode=capi.ABS_INT_TRUNC, q13_mode=capi.Q13_ZERO_Z, max_interactions=128)
     if w == "sedov128": run(w, IC.sedov(128), "sedov3d", steps=3)
