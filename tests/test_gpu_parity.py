@@ -37,7 +37,14 @@ def test_one_step_matches_oracle(case, abs_mode):
     skip = None
     if ic["periodic"]:
         skip = orc_full.fetch("one_sided").astype(bool)  # quirk Q9: the reference reads stale memory there
-    w2 = parity.compare_state(ic, orc_full, gpu, skip=skip)
+    # Exact cubic lattice + integer abs (quirk Q1) + quirk Q13: for neighbours displaced purely along z the pairwise
+    # limiter of the reference divides by |x_j - x_i| = 0 and reconstructs transverse face velocities of +-5.1 in a
+    # fluid at rest (sound speed 1e-3).  The normal velocity of such a face is the round-off residue of rotating those
+    # (1e-15), and the energy flux rho v^2/2 u* A built on it is noise of size 1e-16 that the reference and the GPU
+    # round differently (tools/diag_face.py: pair 4083-4084, F_E -1.8e-16 vs -2.2e-16 from bit-identical states).
+    # It moves u = 1e-6 of those background particles by 3e-10 relative: measured against the field's scale there.
+    scaled = ("u",) if (case == "sedov_lattice_16" and abs_mode == capi.ABS_INT_TRUNC) else ()
+    w2 = parity.compare_state(ic, orc_full, gpu, skip=skip, scaled=scaled)
     print(case, abs_mode, {k: "%.1e" % v for k, v in {**w1, **w2}.items()})
 
 
