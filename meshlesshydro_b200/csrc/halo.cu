@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_halo_pack(const Params p, int lo, int h
                                                    double *buf, int *idbuf, int cap, int *counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.ncur) return;
-    const Grid &g = p.grid;
+    const Grid &g = *p.d.grid;
     const int L = g.cells[g.slab_dim];
     const int l = global_layer(g, p.d.cx[g.slab_dim][i]);
     int below = lo - 1, above = hi; // layers just outside the slab

@@ -19,7 +19,7 @@ template <int D>
 __global__ void __launch_bounds__(256) k_cell_key(const Params p) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.ncur) return;
-    const Grid &g = p.grid;
+    const Grid &g = *p.d.grid;
     int idx[3] = {0, 0, 0};
     bool bad = false;
 #pragma unroll
@@ -182,7 +182,9 @@ int mlh_exclusive_scan(mlh_ctx *c, const int *in, int *out, int *tmp, int n) {
 
 int mlh_launch_sort(mlh_ctx *c) {
     Params &p = c->p;
-    const int n = p.ncur, nc = p.grid.ncells;
+    // the scan covers the whole allocated cell array: counts beyond the grid's last cell are zero, so every entry from
+    // cell_start[ncells] on equals n -- the kernels never need the host to know ncells (device-built grid)
+    const int n = p.ncur, nc = c->max_cells - 1;
     cudaStream_t st = c->stream;
     MLH_CUDA_CHECK(c, cudaMemsetAsync(p.d.cell_count, 0, sizeof(int) * (size_t)(nc + 1), st));
     mlh_prof_begin(c, KID_KEY);

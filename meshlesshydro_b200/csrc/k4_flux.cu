@@ -638,32 +638,28 @@ template <int D> struct FaceRec {
 #define MLH_FACE_TILE 128
 
 // ---------------------------------------------------------------------------------------------
-// face list: fa/fe for the owned slots, global face index for the others
+// face list: the owner of every pair numbers the face and tells its partner
 // ---------------------------------------------------------------------------------------------
-// Thread per particle.  Owned slots get their face number and enter the face list.  For a slot owned by the partner j,
-// K2 left (stencil cell c of this particle as j sees it, index li of this particle inside its cell): j's list is ordered
-// stencil cell by stencil cell and ascending inside a cell, so this particle sits at slot
-// grp[c][j] + popcount(nbm[c][j] & bits below li), and the face is the one j numbered for that slot -- no search.
-// [Searching j's list instead cost 0.27-0.42 ms at 61^3, L1-tag / latency bound: profiles/r01h, r01m.]  Periodic-image
-// slots (few) are found by scanning j's image entries.
+// Thread per particle, four list slots per trip.  K2 left, in every OWNED slot, the rank of the slot among the owner's
+// owned slots and where the partner j keeps the pair: j's list is ordered stencil cell by stencil cell and ascending
+// inside a cell, so this particle sits there at slot grp[cell of i as j sees it][j] + r (r = particles of i's cell
+// below i that list j, counted by K2's ballots).  The owner writes fa/fe, turns its own map entry into the global face
+// index and stores the same index (with the "adds -F" bit) into the partner's slot: ONE gather (grp) and one scattered
+// store per face, nothing for the slots a particle does not own.  [Before: every non-owned slot chased group start,
+// member mask, list length and face base of its partner -- five dependent gathers, 0.10 ms at 61^3,
+// profiles/r02_k_face_index_ncu_full.txt; a search of the partner's list cost 0.27-0.42 ms, profiles/r01h.]
+// Periodic-image slots (few) and cells of more than 32 particles find the partner's slot by scanning its list.
 template <bool PER>
 __global__ void __launch_bounds__(128) k_face_index(const Params p) {
     const int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.own_end) return;
     const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
     const int fs = p.d.face_start[i];
+    const int max_ni = p.max_ni;
     bool over = false;
-    // the slot computed from group start + mask is re-checked against the partner's list only if some list of this step
-    // was cut at max_interactions (flag raised by K2, earlier on this stream): otherwise the relation is symmetric and
-    // the check would be one more gather per slot for nothing
-    const bool verify = (*p.d.flags & MLH_F_MAX_INTERACTIONS) != 0u;
-    // Four slots per trip: a partner-owned slot is a chain of dependent gathers (entry -> j's group start, mask and list
-    // length -> j's slot -> its face), latency-bound one at a time; the four chains of a trip are independent.
     for (int s0 = 0; s0 < ntot; s0 += 4) {
         unsigned v[4], g0[4];
-        unsigned long long nb[4];
-        int e[4], nrj[4], fsj[4];
-        bool fast[4];
+        int e[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int s = s0 + q < ntot ? s0 + q : ntot - 1;
@@ -672,80 +668,50 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
             e[q] = p.d.nnl[at];
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int j = e[q] & MLH_NNL_IDX_MASK;
-            const bool partner = !(v[q] & 2u) && (!PER || s0 + q < nreg);
-            fast[q] = false;
-            if (partner) {
-                const int c = (int)(v[q] >> 14);
-                g0[q] = p.d.grp[(size_t)c * p.ncap + j];
-                nb[q] = p.d.nbm[(size_t)c * p.ncap + j];
-                nrj[q] = p.d.noi[j];
-                fsj[q] = p.d.face_start[j];
-                fast[q] = !(g0[q] & 0x8000u) && (int)((v[q] >> 2) & 0xFFFu) < 64;
-            }
-        }
-        int t[4];
-        unsigned vj[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            t[q] = -1;
-            if (fast[q]) {
-                const int j = e[q] & MLH_NNL_IDX_MASK;
-                const int li = (int)((v[q] >> 2) & 0xFFFu);
-                const int tt = (int)g0[q] + __popcll(nb[q] & ((1ull << li) - 1ull));
-                if (tt < nrj[q]) {
-                    t[q] = tt;
-                    vj[q] = p.d.fmap[(size_t)tt * p.ncap + j]; // owned by j: rank << 2 | 2 | sign
-                    if (verify && p.d.nnl[(size_t)tt * p.ncap + j] != i) t[q] = -1; // j's list was cut at max_interactions
-                }
-            }
+        for (int q = 0; q < 4; ++q) { // the four gathers of a trip are independent
+            g0[q] = 0u;
+            if ((v[q] & MLH_K2_OWNED) && !(v[q] & (MLH_K2_NOPARTNER | MLH_K2_GHOST)))
+                g0[q] = p.d.grp[(size_t)((v[q] >> MLH_K2_SC_SHIFT) & 31u) * p.ncap + (e[q] & MLH_NNL_IDX_MASK)];
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int s = s0 + q;
             if (s >= ntot) break;
+            if (!(v[q] & MLH_K2_OWNED)) continue; // the partner owns the pair: it fills this slot
             const size_t at = (size_t)s * p.ncap + i;
-            const int j = e[q] & MLH_NNL_IDX_MASK;
-            if (v[q] & 2u) {
-                const int f = fs + (int)(v[q] >> 2);
-                if (f < p.fcap) {
-                    p.d.fa[f] = i | (int)((v[q] & 1u) << 31); // bit 31: the partner is the canonical endpoint (lower original index)
-                    p.d.fe[f] = e[q];
-                } else {
-                    over = true;
-                }
+            const unsigned sign = v[q] & 1u;
+            const int f = fs + (int)((v[q] >> MLH_K2_RANK_SHIFT) & MLH_K2_RANK_MASK);
+            if (f >= p.fcap) {
+                over = true;
+                p.d.fmap[at] = MLH_FMAP_SKIP;
                 continue;
             }
-            int tq = t[q];
-            unsigned vjq = vj[q];
-            int fsjq = fsj[q];
-            if (!fast[q]) { // crowded cell or periodic image: scan j's list
-                if (!PER || s < nreg) {
-                    const int nr = p.d.noi[j];
-                    for (int k = (int)(g0[q] & 0x7FFFu); k < nr; ++k)
-                        if (p.d.nnl[(size_t)k * p.ncap + j] == i) {
-                            tq = k;
-                            break;
-                        }
-                } else {
-                    const int want = i | (reverse_code((int)((unsigned)e[q] >> MLH_NNL_IDX_BITS)) << MLH_NNL_IDX_BITS);
-                    const int nr = p.d.noi[j], nt = nr + p.d.noig[j];
-                    for (int k = nr; k < nt; ++k)
-                        if (p.d.nnl[(size_t)k * p.ncap + j] == want) {
-                            tq = k;
-                            break;
-                        }
-                }
-                if (tq >= 0) vjq = p.d.fmap[(size_t)tq * p.ncap + j];
-                fsjq = p.d.face_start[j];
+            p.d.fa[f] = i | (int)(sign << 31); // bit 31: the partner is the canonical endpoint (lower original index)
+            p.d.fe[f] = e[q];
+            p.d.fmap[at] = ((unsigned)f << 2) | MLH_K2_OWNED | sign;
+            if (v[q] & MLH_K2_NOPARTNER) continue;
+            const int j = e[q] & MLH_NNL_IDX_MASK;
+            int t = -1;
+            if (PER && (v[q] & MLH_K2_GHOST)) { // image of j in this list <-> image of i (opposite shift) in j's list
+                const int want = i | (reverse_code((int)((unsigned)e[q] >> MLH_NNL_IDX_BITS)) << MLH_NNL_IDX_BITS);
+                const int nr = p.d.noi[j], nt = nr + p.d.noig[j];
+                for (int k = nr; k < nt; ++k)
+                    if (p.d.nnl[(size_t)k * p.ncap + j] == want) {
+                        t = k;
+                        break;
+                    }
+            } else if (!(v[q] & MLH_K2_R_OVER)) {
+                t = (int)g0[q] + (int)((v[q] >> MLH_K2_R_SHIFT) & 31u);
+                if (t >= max_ni) t = -1; // j's list was cut at max_interactions before this pair
+            } else {
+                const int nr = p.d.noi[j];
+                for (int k = (int)g0[q]; k < nr; ++k)
+                    if (p.d.nnl[(size_t)k * p.ncap + j] == i) {
+                        t = k;
+                        break;
+                    }
             }
-            unsigned res = MLH_FMAP_SKIP;
-            if (tq >= 0)
-                res = ((unsigned)(fsjq + (int)(vjq >> 2)) << 2) | 1u;
-            else
-                over = true; // (MLH_F_MAX_INTERACTIONS is raised by K2 as well)
-            p.d.fmap[at] = res;
+            if (t >= 0) p.d.fmap[(size_t)t * p.ncap + j] = ((unsigned)f << 2) | 1u; // the partner adds -F
         }
     }
     if (over) atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
@@ -1328,7 +1294,6 @@ __global__ void __launch_bounds__(128) k_flux_sum_update(const Params p, double 
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.d.dt_used = dt;
     if (i < p.own_end) {
     const int ntot = p.d.noi[i] + p.d.noig[i];
-    const int fs = p.d.face_start[i];
     double acc[NW];
 #pragma unroll
     for (int nu = 0; nu < NW; ++nu) acc[nu] = 0.;
@@ -1341,8 +1306,8 @@ __global__ void __launch_bounds__(128) k_flux_sum_update(const Params p, double 
         for (int q = 0; q < 4; ++q) v[q] = s0 + q < ntot ? p.d.fmap[(size_t)(s0 + q) * p.ncap + i] : MLH_FMAP_SKIP;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int f = (v[q] & 2u) ? fs + (int)(v[q] >> 2) : (int)(v[q] >> 2);
-            if (v[q] == MLH_FMAP_SKIP || f >= p.fcap) { // no face / face capacity exceeded (flag raised by k_face_index)
+            const int f = (int)(v[q] >> 2);
+            if (v[q] == MLH_FMAP_SKIP || f >= p.fcap) { // no face (the other side's list was cut at capacity)
                 v[q] = MLH_FMAP_SKIP;
                 continue;
             }
@@ -1422,6 +1387,7 @@ __global__ void __launch_bounds__(128) k_flux_sum_update(const Params p, double 
             } else {
                 p.d.bbox[6 + k] = xs[k];
             }
+            if (id == 1) p.d.bbox[9 + k] = xs[k];
         }
     }
     }
@@ -1478,6 +1444,7 @@ int launch_chunks(mlh_ctx *c, double dt_fixed, double dt_max) {
 int mlh_launch_face_index(mlh_ctx *c) {
     Params &p = c->p;
     const int n = p.own_end - p.own_begin;
+    if (n <= 0) return MLH_OK;
     mlh_prof_begin(c, KID_FACE_INDEX);
     // face_start is indexed by the SRT index; entries below own_begin are never read
     mlh_exclusive_scan(c, p.d.nown + p.own_begin, p.d.face_start + p.own_begin, p.d.face_scan_tmp, n);

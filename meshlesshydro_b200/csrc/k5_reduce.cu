@@ -15,6 +15,7 @@ __global__ void k_bbox_init(const Params p) {
         keys[k] = dbl_key(DBL_MAX);     // running minimum starts at numeric_limits::max()  (:230)
         keys[3 + k] = dbl_key(DBL_MIN); // running maximum starts at numeric_limits::min()  (:231, quirk Q2)
         p.d.bbox[6 + k] = -DBL_MAX;     // coordinate of original particle 0 (set by whoever owns it)
+        p.d.bbox[9 + k] = -DBL_MAX;     // coordinate of original particle 1 (multi-GPU form of quirk Q8, mlh_capi.cu)
     }
 }
 
@@ -29,13 +30,15 @@ __global__ void __launch_bounds__(256) k_bbox(const Params p) {
         mx[k] = DBL_MIN;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.ncur; i += gridDim.x * blockDim.x) {
-        const bool first = p.d.cid[i] == 0;
+        const int id = p.d.cid[i];
+        const bool first = id == 0;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             double x = p.d.cx[k][i];
             mn[k] = x < mn[k] ? x : mn[k];
             if (!first) mx[k] = x > mx[k] ? x : mx[k];
             else p.d.bbox[6 + k] = x;
+            if (id == 1) p.d.bbox[9 + k] = x;
         }
     }
     mlh_bbox_block_reduce<D>(p, mn, mx);
@@ -64,6 +67,80 @@ __global__ void k_bbox_replay(const Params p, const int *inv) {
     }
     keys[k] = dbl_key(mn);
     keys[3 + k] = dbl_key(mx);
+}
+
+// Domain::createGrid (Domain.cpp:9-54) on the device, fed by the bounding box the update kernel of the previous step
+// reduced (getDomainLimits, Particles.cpp:228-267): non-periodic runs rebuild the search grid every step
+// (MeshlessScheme.cpp:41-51) and no longer stop the stream for it.  One block: if original particle 0 is the strict
+// maximum along an axis (quirk Q8) the block first builds the id -> index table and that axis is replayed in original
+// order, exactly as the reference's sequential loop.  The arithmetic is the host's (make_grid, mlh_capi.cu): IEEE
+// subtract, divide, floor.  A grid that does not fit the allocated cell arrays raises MLH_F_OUT_OF_GRID and leaves the
+// previous grid in place (the host grows the arrays from its one-step-late mirror long before that).
+template <int D>
+__global__ void __launch_bounds__(1024) k_make_grid(const Params p, int max_cells) {
+    __shared__ int need;
+    unsigned long long *keys = (unsigned long long *)p.d.bbox;
+    if (threadIdx.x == 0) {
+        // the reduction (min over all, max over original index >= 1) differs from the sequential loop only if the largest
+        // coordinate among the indices >= 1 belongs to particle 1 AND lies below particle 0 (see mlh_build_grid)
+        int nd = 0;
+        for (int k = 0; k < D; ++k) {
+            const double m1 = key_dbl(keys[3 + k]);
+            nd |= (p.d.bbox[6 + k] > m1 && p.d.bbox[9 + k] >= m1) ? 1 : 0;
+        }
+        need = nd;
+    }
+    __syncthreads();
+    if (need) {
+        int *inv = p.d.perm; // free before the sort
+        for (int i = threadIdx.x; i < p.ncur; i += blockDim.x) inv[p.d.cid[i]] = i;
+        __syncthreads();
+        if (threadIdx.x < D) {
+            const int k = threadIdx.x;
+            const double m1 = key_dbl(keys[3 + k]);
+            if (p.d.bbox[6 + k] > m1 && p.d.bbox[9 + k] >= m1) {
+                double mn = DBL_MAX, mx = DBL_MIN;
+                for (int id = 0; id < p.ncur; ++id) {
+                    const double x = p.d.cx[k][inv[id]];
+                    if (x < mn)
+                        mn = x;
+                    else if (x > mx)
+                        mx = x;
+                }
+                keys[k] = dbl_key(mn);
+                keys[3 + k] = dbl_key(mx);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        Grid g = *p.d.grid;
+        long long nc = 1;
+        bool ok = true;
+        for (int k = 0; k < D; ++k) {
+            const double lo = key_dbl(keys[k]), hi = key_dbl(keys[3 + k]);
+            const double cells = floor(__ddiv_rn(__dsub_rn(hi, lo), p.h));
+            if (!(cells >= 1.) || cells > 2.0e9) {
+                ok = false;
+                break;
+            }
+            g.bmin[k] = lo;
+            g.bmax[k] = hi;
+            g.cells[k] = g.lcells[k] = (int)cells;
+            g.cell_size[k] = __ddiv_rn(__dsub_rn(hi, lo), (double)g.cells[k]);
+            nc *= g.cells[k];
+            if (nc + 1 > (long long)max_cells) {
+                ok = false;
+                break;
+            }
+        }
+        if (ok) {
+            g.ncells = (int)nc;
+            *p.d.grid = g;
+        } else {
+            atomicOr(p.d.flags, MLH_F_OUT_OF_GRID);
+        }
+    }
 }
 
 // sums over the CUR set (state) -- V uses omega of the SRT set (same order)
@@ -133,6 +210,17 @@ int mlh_launch_bbox_q8_replay(mlh_ctx *c) {
     else
         k_bbox_replay<3><<<1, 32, 0, c->stream>>>(p, p.d.perm);
     c->launches += 2;
+    MLH_CUDA_CHECK(c, cudaGetLastError());
+    return MLH_OK;
+}
+
+int mlh_launch_make_grid(mlh_ctx *c) {
+    Params &p = c->p;
+    if (p.D == 2)
+        k_make_grid<2><<<1, 1024, 0, c->stream>>>(p, c->max_cells);
+    else
+        k_make_grid<3><<<1, 1024, 0, c->stream>>>(p, c->max_cells);
+    c->launches += 1;
     MLH_CUDA_CHECK(c, cudaGetLastError());
     return MLH_OK;
 }

@@ -87,8 +87,9 @@ static void carve_pool(mlh_ctx *c, Carver &cv) {
     d.ckey = cv.take<int>(n); d.crank = cv.take<int>(n); d.perm = cv.take<int>(n);
     d.nnl = cv.take<int>(n * (size_t)p.max_ni);
     d.fmap = cv.take<unsigned>(n * (size_t)p.max_ni);
+    d.wc = cv.take<double>(n * (size_t)p.max_ni);
+    d.rc = cv.take<double>(n * (size_t)p.max_ni);
     d.grp = cv.take<unsigned short>(n * (size_t)27);
-    d.nbm = cv.take<unsigned long long>(n * (size_t)27);
     d.nown = cv.take<int>(n);
     d.face_start = cv.take<int>(n + 1);
     d.face_scan_tmp = cv.take<int>(n / 1024 + 4);
@@ -105,7 +106,8 @@ static void carve_pool(mlh_ctx *c, Carver &cv) {
     }
     d.dt_bits = cv.take<unsigned long long>(1);
     d.dt_used = cv.take<double>(1);
-    d.bbox = cv.take<double>(9);
+    d.bbox = cv.take<double>(12);
+    d.grid = cv.take<Grid>(1);
     d.sums = cv.take<double>(6);
     d.flags = cv.take<unsigned>(1);
     d.counters = cv.take<unsigned>(4);
@@ -159,18 +161,34 @@ static int make_grid(mlh_ctx *c, const double *bmin, const double *bmax) {
         return MLH_E_INVALID;
     }
     g.ncells = (int)nc;
-    if (g.ncells + 1 > c->max_cells) {
-        if (p.d.cell_count) {
-            cudaStreamSynchronize(c->stream);
-            cudaFree(p.d.cell_count);
-            cudaFree(p.d.cell_start);
-            cudaFree(p.d.scan_tmp);
-        }
-        c->max_cells = (int)std::min<long long>(2147483647LL, (long long)((g.ncells + 1) * 1.25) + 1024);
-        MLH_CUDA_CHECK(c, cudaMalloc(&p.d.cell_count, sizeof(int) * (size_t)c->max_cells));
-        MLH_CUDA_CHECK(c, cudaMalloc(&p.d.cell_start, sizeof(int) * (size_t)c->max_cells));
-        MLH_CUDA_CHECK(c, cudaMalloc(&p.d.scan_tmp, sizeof(int) * (size_t)(c->max_cells / 1024 + 2)));
+    return MLH_OK;
+}
+
+// host grid -> device copy read by K1 / K2 / the halo kernels (pinned staging: the caller has just synchronised the
+// stream or is outside the time loop, so the staging buffer is not in flight)
+static int upload_grid(mlh_ctx *c) {
+    if (!c->pool) return MLH_OK; // done by mlh_upload once the pool exists
+    c->h_grid[0] = c->p.grid;
+    MLH_CUDA_CHECK(c, cudaMemcpyAsync(c->p.d.grid, &c->h_grid[0], sizeof(Grid), cudaMemcpyHostToDevice, c->stream));
+    c->grid_host_current = true;
+    c->grid_mirror_pending = false;
+    return MLH_OK;
+}
+
+// cell arrays for at least `need` entries (cell_count / cell_start / scan_tmp); synchronises when it has to grow
+static int reserve_cells(mlh_ctx *c, long long need) {
+    Params &p = c->p;
+    if (need <= c->max_cells) return MLH_OK;
+    if (p.d.cell_count) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(p.d.cell_count);
+        cudaFree(p.d.cell_start);
+        cudaFree(p.d.scan_tmp);
     }
+    c->max_cells = (int)std::min<long long>(2147483647LL, (long long)(need * 1.25) + 1024);
+    MLH_CUDA_CHECK(c, cudaMalloc(&p.d.cell_count, sizeof(int) * (size_t)c->max_cells));
+    MLH_CUDA_CHECK(c, cudaMalloc(&p.d.cell_start, sizeof(int) * (size_t)c->max_cells));
+    MLH_CUDA_CHECK(c, cudaMalloc(&p.d.scan_tmp, sizeof(int) * (size_t)(c->max_cells / 1024 + 2)));
     return MLH_OK;
 }
 
@@ -365,6 +383,8 @@ int mlh_create(const mlh_config *cfg, mlh_ctx **out) {
     cudaEventCreate(&c->timer[0]);
     cudaEventCreate(&c->timer[1]);
     cudaMallocHost(&c->h_small, 64 * sizeof(double));
+    cudaMallocHost(&c->h_grid, 2 * sizeof(Grid)); // [0] host -> device staging, [1] asynchronous mirror of the device grid
+    cudaEventCreateWithFlags(&c->ev_grid, cudaEventDisableTiming);
     cudaMallocHost(&c->h_flags, 8 * sizeof(unsigned));
     if (p.periodic) {
         double bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
@@ -373,6 +393,7 @@ int mlh_create(const mlh_config *cfg, mlh_ctx **out) {
             bmax[k] = cfg->box[p.D + k];
         }
         int rc = make_grid(c, bmin, bmax); // MeshlessScheme.cpp:17
+        if (rc == MLH_OK) rc = reserve_cells(c, (long long)c->p.grid.ncells + 2);
         if (rc != MLH_OK) {
             snprintf(g_create_err, sizeof(g_create_err), "%s", c->err);
             mlh_destroy(c);
@@ -401,6 +422,8 @@ int mlh_destroy(mlh_ctx *c) {
     cudaEventDestroy(c->timer[1]);
     cudaFreeHost(c->h_small);
     cudaFreeHost(c->h_flags);
+    cudaFreeHost(c->h_grid);
+    cudaEventDestroy(c->ev_grid);
     cudaStreamDestroy(c->stream);
     delete c;
     return MLH_OK;
@@ -436,6 +459,10 @@ int mlh_upload(mlh_ctx *c, long N, const double *x, const double *y, const doubl
     long cap = c->cfg.capacity > 0 ? c->cfg.capacity : (c->cfg.nranks > 1 ? N + N / 2 + 4096 : N);
     if (cap < N) cap = N;
     cap = (long)align_up((size_t)cap, 32);
+    if ((unsigned long long)cap * (unsigned long long)p.max_ni >= (1ull << 32)) { // slot arrays are indexed with 32 bits
+        snprintf(c->err, sizeof(c->err), "mlh_upload: capacity %ld x max_interactions %d exceeds 2^32 list slots: lower max_interactions", cap, p.max_ni);
+        return MLH_E_INVALID;
+    }
     if (!c->pool || cap > c->capacity) {
         if (c->pool) {
             cudaStreamSynchronize(c->stream);
@@ -483,6 +510,11 @@ int mlh_upload(mlh_ctx *c, long N, const double *x, const double *y, const doubl
     }
     MLH_CUDA_CHECK(c, cudaMemsetAsync(p.d.flags, 0, sizeof(unsigned), st));
     MLH_CUDA_CHECK(c, cudaMemsetAsync(p.d.counters, 0, 4 * sizeof(unsigned), st));
+    c->grid_host_current = false;
+    if (p.periodic) { // fixed grid (MeshlessScheme.cpp:17): the device copy follows the pool
+        int rcg = upload_grid(c);
+        if (rcg != MLH_OK) return rcg;
+    }
     MLH_CUDA_CHECK(c, cudaStreamSynchronize(st));
     p.ncur = (int)N;
     p.n = 0;
@@ -506,35 +538,66 @@ int mlh_build_grid(mlh_ctx *c) {
     if (!p.periodic) { // MeshlessScheme.cpp:41-51: grid rebuilt from the particle bounding box every step
         // the update kernel of the previous step has already reduced the box of its new positions (k_flux_sum_update);
         // a freshly uploaded state needs the stand-alone pass
-        int rc = c->bbox_valid ? MLH_OK : mlh_launch_bbox(c);
-        if (rc != MLH_OK) return rc;
-        c->bbox_valid = false;
-        if (multi && (rc = mlh_comm_bbox(c)) != MLH_OK) return rc;
-        MLH_CUDA_CHECK(c, cudaMemcpyAsync(c->h_small, p.d.bbox, 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        MLH_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-        for (int k = 0; k < 6; ++k) { // [0..5] travel as order-preserving keys
-            unsigned long long key;
-            memcpy(&key, &c->h_small[k], sizeof(key));
-            c->h_small[k] = key_dbl(key);
-        }
-        bool q8 = false; // original particle 0 is the strict maximum along an axis: sequential replay needed
-        for (int k = 0; k < p.D; ++k) q8 = q8 || c->h_small[6 + k] > c->h_small[3 + k];
-        if (q8) {
-            if (multi) {
-                snprintf(c->err, sizeof(c->err), "getDomainLimits quirk Q8 (particle 0 is an axis maximum) is not supported with nranks > 1");
-                return MLH_E_INVALID;
+        if (!multi && c->bbox_valid && c->max_cells > 0 && p.grid.ncells > 0) {
+            // ---- single GPU, inside the time loop: Domain::createGrid runs on the device, no host round trip ----
+            c->bbox_valid = false;
+            if (c->grid_mirror_pending && cudaEventQuery(c->ev_grid) == cudaSuccess) {
+                // the grid of an earlier step has arrived: keep the cell arrays well ahead of it
+                p.grid = c->h_grid[1];
+                c->grid_mirror_pending = false;
+                if ((long long)p.grid.ncells + 2 > (long long)(0.8 * c->max_cells)) {
+                    int rcr = reserve_cells(c, 2LL * p.grid.ncells + 2);
+                    if (rcr != MLH_OK) return rcr;
+                }
+            } else {
+                cudaGetLastError(); // cudaErrorNotReady is not an error
             }
-            if ((rc = mlh_launch_bbox_q8_replay(c)) != MLH_OK) return rc;
-            MLH_CUDA_CHECK(c, cudaMemcpyAsync(c->h_small, p.d.bbox, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            int rc = mlh_launch_make_grid(c);
+            if (rc != MLH_OK) return rc;
+            c->grid_host_current = false;
+            if (!c->grid_mirror_pending) {
+                MLH_CUDA_CHECK(c, cudaMemcpyAsync(&c->h_grid[1], p.d.grid, sizeof(Grid), cudaMemcpyDeviceToHost, c->stream));
+                MLH_CUDA_CHECK(c, cudaEventRecord(c->ev_grid, c->stream));
+                c->grid_mirror_pending = true;
+            }
+        } else {
+            int rc = c->bbox_valid ? MLH_OK : mlh_launch_bbox(c);
+            if (rc != MLH_OK) return rc;
+            c->bbox_valid = false;
+            if (multi && (rc = mlh_comm_bbox(c)) != MLH_OK) return rc;
+            MLH_CUDA_CHECK(c, cudaMemcpyAsync(c->h_small, p.d.bbox, 12 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             MLH_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-            for (int k = 0; k < 6; ++k) {
+            for (int k = 0; k < 6; ++k) { // [0..5] travel as order-preserving keys
                 unsigned long long key;
                 memcpy(&key, &c->h_small[k], sizeof(key));
                 c->h_small[k] = key_dbl(key);
             }
+            // quirk Q8: the sequential `if (x<min) .. else if (x>max)` loop never tests a particle that lowers the running
+            // minimum against the maximum.  The reduction above (min over all, max over original index >= 1) equals it
+            // unless the largest coordinate among the indices >= 1 is itself such a record low -- which, given that it is
+            // the largest, can only be original particle 1 sitting below particle 0.
+            bool q8 = false;
+            for (int k = 0; k < p.D; ++k) q8 = q8 || (c->h_small[6 + k] > c->h_small[3 + k] && c->h_small[9 + k] >= c->h_small[3 + k]);
+            if (q8) {
+                if (multi) {
+                    snprintf(c->err, sizeof(c->err), "getDomainLimits quirk Q8: original particles 0 and 1 are the two largest along an axis -- "
+                                                     "the sequential replay is not supported with nranks > 1");
+                    return MLH_E_INVALID;
+                }
+                if ((rc = mlh_launch_bbox_q8_replay(c)) != MLH_OK) return rc;
+                MLH_CUDA_CHECK(c, cudaMemcpyAsync(c->h_small, p.d.bbox, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                MLH_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+                for (int k = 0; k < 6; ++k) {
+                    unsigned long long key;
+                    memcpy(&key, &c->h_small[k], sizeof(key));
+                    c->h_small[k] = key_dbl(key);
+                }
+            }
+            rc = make_grid(c, c->h_small, c->h_small + 3);
+            if (rc == MLH_OK) rc = reserve_cells(c, (long long)p.grid.ncells + 2);
+            if (rc == MLH_OK) rc = upload_grid(c);
+            if (rc != MLH_OK) return rc;
         }
-        rc = make_grid(c, c->h_small, c->h_small + 3);
-        if (rc != MLH_OK) return rc;
     }
     if (multi) { // exchange 1: boundary layers + migrants (createGhostParticles point of the step)
         int rc = mlh_halo_exchange_particles(c);
@@ -651,6 +714,14 @@ long mlh_num_particles(mlh_ctx *c) { return c ? c->n_owned : -1; }
 
 int mlh_grid_info(mlh_ctx *c, int *cells3, double *cell_size3, double *bounds6) {
     if (!c) return MLH_E_INVALID;
+    if (!c->grid_host_current && c->pool && c->p.grid.ncells > 0) { // the device built the grid of this step: fetch it
+        cudaSetDevice(c->cfg.device);
+        if (cudaMemcpyAsync(&c->h_grid[0], c->p.d.grid, sizeof(Grid), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess)
+            return MLH_E_CUDA;
+        c->p.grid = c->h_grid[0];
+        c->grid_host_current = true;
+    }
     const Grid &g = c->p.grid;
     for (int k = 0; k < 3; ++k) {
         if (cells3) cells3[k] = g.cells[k];

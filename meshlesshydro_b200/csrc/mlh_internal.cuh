@@ -14,11 +14,15 @@
 //   faces:   every pair (i,j) of the lists is ONE face, owned by exactly one of its endpoints (the one
 //            with the lower ORIGINAL index; always self when the partner is a halo particle of
 //            another rank or does not list the pair, quirk Q9).  fmap (slot-major like nnl) maps
-//            each list slot to its face: bits [2..31] value, bit 1 = owned (value = rank among the
-//            owner's owned slots, face index = face_start[i] + rank), else value = global face
-//            index; bit 0 = this endpoint adds -F.  Between K2 and k_face_index a partner-owned slot holds
-//            (index of the particle inside its own cell | mirrored stencil cell << 12).  fa/fe = owner index and list entry of face f;
-//            F = fluxes in canonical orientation, AoS MLH_FREC(D) doubles per face.
+//            each list slot to its face: (global face index << 2) | bit 1 = owned by this particle | bit 0 = this
+//            endpoint adds -F; MLH_FMAP_SKIP = no face.  Between K2 and k_face_index an OWNED slot holds the
+//            MLH_K2_* word below (rank among the owner's slots + where the partner keeps the pair); the owner then
+//            numbers the face and writes the index into the partner's slot as well.  fa/fe = owner index and list
+//            entry of face f; F = fluxes in canonical orientation, AoS MLH_FREC(D) doubles per face.
+//   grp:     grp[c*ncap + i] = first slot of stencil cell c (reference order, Domain.cpp:83-118) in the list of i.
+//            The list of j is ordered stencil cell by stencil cell and ascending inside a cell, so particle i of
+//            cell C sits in j's list at grp[mirror(c)][j] + (number of particles of C below i that list j) -- the
+//            second term is counted by the warp that searches cell C (k2_neighbours.cu): no reverse search.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -32,7 +36,15 @@
 #define MLH_NNL_IDX_MASK ((1 << MLH_NNL_IDX_BITS) - 1)
 #define MLH_FREC(D) ((D) == 2 ? 4 : 6)      // doubles per face in the flux array (D+2 used)
 #define MLH_FMAP_SKIP 0xFFFFFFFCu           // slot without a face (partner's list overflowed)
-#define MLH_FMAP_GHOST_SEARCH 0xFFFFFFF8u    // K2 -> k_face_index: periodic-image slot owned by the partner (searched)
+// K2 -> k_face_index word of an owned slot
+#define MLH_K2_OWNED 2u
+#define MLH_K2_RANK_SHIFT 2           // 10 bits: rank of the slot among the owner's owned slots
+#define MLH_K2_RANK_MASK 0x3FFu
+#define MLH_K2_R_SHIFT 12             // 5 bits: particles of the owner's cell below the owner that list the partner
+#define MLH_K2_R_OVER (1u << 17)      // not counted (cell with more than 32 particles): the partner's list is searched
+#define MLH_K2_SC_SHIFT 18            // 5 bits: stencil cell of the owner as the partner sees it
+#define MLH_K2_NOPARTNER (1u << 23)   // the partner keeps no slot for the pair (other rank's halo / one-sided pair)
+#define MLH_K2_GHOST (1u << 24)       // periodic-image slot: the partner's slot is found among its image entries
 
 // constants of the restated exact Riemann solver (same expressions as oracle/riemann_exact.h:rs_init)
 struct RsConsts {
@@ -57,8 +69,7 @@ struct DevPtrs {
     double *B[9];   // Binv row-major as used by the reference (Particles.cpp:1249)
     double *g[15];  // gradients: field f in {0 rho,1 vx,2 vy,3 vz,4 P}; component a -> g[f*3+a]
     int *id, *cell, *noi, *noig, *nnl;
-    unsigned short *grp; // grp[c*ncap + i] = first slot of stencil cell c (reference order) in the list of i (bit 15: cell holds > 64 particles)
-    unsigned long long *nbm; // nbm[c*ncap + i] bit k = i lists the k-th particle of stencil cell c
+    unsigned short *grp; // grp[c*ncap + i] = first slot of stencil cell c (reference order) in the list of i
     // faces (see header comment)
     unsigned *fmap;
     int *nown, *face_start, *face_scan_tmp, *fa, *fe;
@@ -68,6 +79,10 @@ struct DevPtrs {
     //   pk1[i*PK1 ..] = x[D], v[D], rho, P, cs, omega          (written by K3;  PK1 = 2D+4)
     //   pk2[i*PK2 ..] = Binv[D*D] row-major, grad[(D+2)][D] in W order rho,P,vx,vy(,vz)   (written by K3b; PK2 = D*D+(D+2)*D)
     double *pk1, *pk2;
+    // per-slot cache (slot-major like nnl, coalesced for the thread-per-particle sweeps): K3's first sweep stores the
+    // kernel value W(r_ij) and r_ij of every list entry, its second sweep turns W into psi_j(x_i) = W / omega_i, K3b
+    // reads both -- instead of redoing sqrt + division + spline (+ division) per visit in three more sweeps
+    double *wc, *rc;
     // CUR set
     double *cx[3], *cv[3], *cm, *cu;
     int *cid;
@@ -79,7 +94,9 @@ struct DevPtrs {
     double *dbg_face; // debug_capture: per face (AoS, 4D+4 doubles) WijR (canonical endpoint), WijL, vFrame, Aij as K4a formed them
     // reductions
     unsigned long long *dt_bits; // min CFL dt as ordered bit pattern
-    double *bbox;                // [0..2] min, [3..5] max over i>=1 (quirk Q8) as ORDERED KEYS (dbl_key), [6..8] x[0] as doubles
+    double *bbox;                // [0..2] min, [3..5] max over i>=1 (quirk Q8) as ORDERED KEYS (dbl_key), [6..8] x[0], [9..11] x[1] as doubles
+    Grid *grid;                  // the search grid the kernels of K1 / K2 / the halo exchange read (Domain::createGrid on
+                                 // the device for non-periodic single-GPU runs, else a copy of Params::grid)
     double *sums;                // 6 doubles
     unsigned *flags;             // MLH_F_* bits
     unsigned *counters;          // [0] one-sided seam pairs, [3] longest neighbour list of this step (K2)
@@ -297,6 +314,10 @@ struct mlh_ctx {
     long capacity;
     bool have_state;     // mlh_upload done
     bool bbox_valid;     // d.bbox describes the CUR set (reduced by the update kernel of the last step; non-periodic runs)
+    bool grid_host_current; // Params::grid (host) equals *d.grid (device); false while the device builds the grid itself
+    bool grid_mirror_pending; // an asynchronous copy of *d.grid into h_grid is in flight (ev_grid)
+    Grid *h_grid;        // pinned
+    cudaEvent_t ev_grid;
     int phase;           // 0 = CUR valid (start of step); 1..4 after grid/neighbours/density/gradients
     void *pool;          // single device allocation backing all arrays
     size_t pool_bytes;
@@ -342,6 +363,7 @@ int mlh_launch_flux(mlh_ctx *c, double dt_fixed, double dt_max); // k4_flux.cu
 int mlh_launch_sums(mlh_ctx *c);        // k5_reduce.cu
 int mlh_launch_bbox(mlh_ctx *c);        // k5_reduce.cu
 int mlh_launch_bbox_q8_replay(mlh_ctx *c); // k5_reduce.cu (rare path of quirk Q8)
+int mlh_launch_make_grid(mlh_ctx *c);      // k5_reduce.cu: Domain::createGrid on the device (+ the Q8 replay if needed)
 // halo.cu (nranks > 1)
 void mlh_comm_destroy(mlh_ctx *c);
 int mlh_comm_bbox(mlh_ctx *c);
