@@ -97,9 +97,12 @@ __device__ __forceinline__ int global_layer(const Grid &g, double x) {
 template <int D>
 __global__ void __launch_bounds__(256) k_halo_pack(const Params p, int lo, int hi, int periodic, int has_dn, int has_up,
                                                    double *buf, int *idbuf, int cap, int *counts) {
+    __shared__ Grid s_grid;
+    if (threadIdx.x == 0) s_grid = *p.d.grid;
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.ncur) return;
-    const Grid &g = *p.d.grid;
+    const Grid &g = s_grid;
     const int L = g.cells[g.slab_dim];
     const int l = global_layer(g, p.d.cx[g.slab_dim][i]);
     int below = lo - 1, above = hi; // layers just outside the slab

@@ -17,9 +17,12 @@ namespace {
 // IEEE subtract, divide, floor -- no contraction possible).
 template <int D>
 __global__ void __launch_bounds__(256) k_cell_key(const Params p) {
+    __shared__ Grid s_grid; // the grid lives in device memory (device-built in non-periodic runs): one copy per block
+    if (threadIdx.x == 0) s_grid = *p.d.grid;
+    __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.ncur) return;
-    const Grid &g = *p.d.grid;
+    const Grid &g = s_grid;
     int idx[3] = {0, 0, 0};
     bool bad = false;
 #pragma unroll

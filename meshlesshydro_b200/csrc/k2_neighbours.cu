@@ -6,26 +6,28 @@
 //
 // A stencil cell is a contiguous index range of the sorted arrays.  The warp that owns cell C lays the 3^D
 // ranges of its stencil end to end IN THE REFERENCE'S ORDER (x outer, y, z inner; ascending index inside a
-// cell) and cuts that candidate sequence into tiles of 32: lane l of tile t holds candidate 32 t + l
-// (coordinates, original id) in registers, K2_U tiles at a time.  The particles of C -- staged once in shared
-// memory -- are then tested against a tile with ONE instruction stream for 32 candidates: the cutoff
-// `pow(dx,2)+pow(dy,2)[+pow(dz,2)] < h*h` without FMA contraction (dist_sqr_exact), so the SETS are bit-exact;
-// `__ballot_sync` gives the hit mask, and a hit lands in list slot
-//     (hits of this particle so far) + popc(mask & lanes below)
-// -- the list order is the reference's by construction (Particles.cpp:335-359), no sorting, no per-thread
-// walk over 27 ranges.  [The previous thread-per-particle walk: 22 of 32 lanes busy, 614 warp instructions per
-// particle, 0.208 ms at 61^3 -- profiles/r02_k_neighbours_ncu_full.txt.]
-//
-// The same ballots give the face bookkeeping for free (no group masks, no id gathers):
-//   * ownership of the pair = lower ORIGINAL index (Particles.cpp:1841,1889), ids ride with the candidates;
-//   * the rank of the slot among the particle's owned slots = running count + popc(owned mask & lanes below);
-//   * r = how many particles of C BELOW this one list the same candidate j = a per-lane hit counter, because
-//     the particles of C are visited in ascending order.  j's list is ordered stencil cell by stencil cell,
-//     so this particle sits in j's list at grp[mirrored cell][j] + r: k_face_index (k4_flux.cu) finds the
-//     partner's slot with one gather instead of a search;
-//   * the hits of a particle in the tiles at hand are compacted into a shared-memory queue (queue position = list
-//     slot), then written out one lane per hit; where the stencil cell changes between consecutive hits, that lane
-//     also records grp[c][i], the first slot of stencil cell c in the list of i.
+// cell) and cuts that candidate sequence into tiles of 32.  Two phases per cell:
+//   tests     lane l of tile t holds candidate 32 t + l in registers (K2_U tiles at a time); the particles of C --
+//             staged once in shared memory -- are tested against a tile with ONE instruction stream for 32
+//             candidates: the cutoff `pow(dx,2)+pow(dy,2)[+pow(dz,2)] < h*h` without FMA contraction
+//             (dist_sqr_exact), so the SETS are bit-exact.  `__ballot_sync` turns the 32 outcomes into one hit mask
+//             per (particle, tile), parked in shared memory; each lane also collects, per candidate it holds, the
+//             bit mask of the particles that hit it.  12 instructions per 32 tests, nothing data-dependent.
+//             [The previous thread-per-particle walk spent ~11 instructions per candidate at 22 of 32 lanes:
+//             614 warp instructions per particle, 0.208 ms at 61^3, profiles/r02_k_neighbours_ncu_full.txt.]
+//   emission  lane l walks the masks of particle l in candidate order = the reference's list order
+//             (Particles.cpp:335-359): the n-th set bit is list slot n.  All lanes emit their n-th entry in the same
+//             iteration, so slot n of consecutive particles leaves as one contiguous run (the lists are slot-major).
+// The masks also give the face bookkeeping without gathers or searches:
+//   * ownership of the pair = lower ORIGINAL index (Particles.cpp:1841,1889); ids sit in the candidate table;
+//   * r = how many particles of C BELOW this one list the same candidate j = popcount of the candidate's
+//     particle mask below this lane.  j's list is ordered stencil cell by stencil cell, so this particle sits in j's
+//     list at grp[mirrored cell][j] + r: k_face_index (k4_flux.cu) finds the partner's slot with one gather;
+//   * grp[c][i] (first slot of stencil cell c in the list of i) falls out where the stencil cell of consecutive
+//     entries changes.
+// [First version of the warp-per-cell search, profiles/r2c_k_neighbours_cell_v1_*: it emitted the hits of one particle
+// with one lane per hit right after every group of tiles -- 697 warp instructions per particle, 4-byte stores scattered
+// over as many rows as there were hits; 0.261 ms at 61^3 and 1.43 ms at KH 1M against 0.206 / 0.52 ms before.]
 //
 // Periodic images are not materialised as ghost particles: a stencil cell that wraps around the box yields
 // candidates whose image position is computed on the fly with the reference's formulas (image_coord) and whose
@@ -99,9 +101,8 @@ __device__ __forceinline__ void stencil_offset(int k, int *off) {
 // ---- periodic images of one particle (one lane): Particles.cpp:2113-2191 + :2237-2260, appended after the `nreg`
 // regular entries; then the ownership of those slots.  Returns the number of image entries; *nown is advanced. ----
 template <int D>
-__device__ int ghost_entries(const Params &p, int i, int c, int nreg, unsigned *nown_io, bool *overflow) {
+__device__ int ghost_entries(const Params &p, const Grid &g, int i, int c, int nreg, unsigned *nown_io, bool *overflow) {
     constexpr bool PER = true;
-    const Grid &g = *p.d.grid;
     double xi[3];
 #pragma unroll
     for (int k = 0; k < D; ++k) xi[k] = p.d.x[k][i];
@@ -201,26 +202,28 @@ __device__ int ghost_entries(const Params &p, int i, int c, int nreg, unsigned *
 }
 
 constexpr int K2_WARPS = 4;  // warps (= cells in flight) per block
-constexpr int K2_U = 5;      // candidate tiles held in registers at a time (3D: ~9 tiles per cell, 2D: 4-5)
-constexpr int K2_MAXCH = 32; // tiles per cell: 1024 candidates; a denser stencil overflows every list anyway
-constexpr int K2_MAXP = 32;  // particles of the cell per pass
-
-// per-particle progress word carried by lane l for particle l of the pass
-__device__ __forceinline__ unsigned k2_pack(unsigned cnt, unsigned nown, unsigned gk) { return cnt | (nown << 11) | (gk << 22); }
+constexpr int K2_U = 4;      // candidate tiles held in registers at a time
+constexpr int K2_MAXCH = 16; // tiles per pass over the candidates: 512 (3D: ~280 per cell, 2D: ~140); denser cells take more passes
+constexpr int K2_MAXP = 32;  // particles of the cell per batch
 
 template <int D, bool PER>
 __global__ void __launch_bounds__(32 * K2_WARPS) k_neighbours_cell(const Params p) {
     constexpr int NS = D == 3 ? 27 : 9;
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr unsigned KEEP = (31u << MLH_K2_R_SHIFT) | MLH_K2_R_OVER | (31u << MLH_K2_SC_SHIFT) | MLH_K2_NOPARTNER;
-    __shared__ double s_x[K2_WARPS][D][K2_MAXP];     // the cell's own particles
-    __shared__ int s_qj[K2_WARPS][32 * K2_U];        // hits of the current particle in the current tiles: sorted index ..
-    __shared__ unsigned s_qi[K2_WARPS][32 * K2_U];   // .. and pair info (MLH_K2_* bits, bit 0 = the partner has the lower id)
-    __shared__ int s_off[K2_WARPS][NS + 1];          // first candidate number of each stencil cell
-    __shared__ int s_start[K2_WARPS][NS];            // first sorted index of each stencil cell
+    __shared__ Grid s_grid;                                   // the search grid (device-built in non-periodic runs)
+    __shared__ double s_x[K2_WARPS][D][K2_MAXP];              // the cell's own particles
+    __shared__ unsigned s_j[K2_WARPS][32 * K2_MAXCH];         // candidate: sorted index | mirrored stencil cell << 26 | other rank's halo << 31
+    __shared__ int s_id[K2_WARPS][32 * K2_MAXCH];             // candidate: original id
+    __shared__ unsigned s_col[K2_WARPS][32 * K2_MAXCH];       // candidate: which particles of the batch list it (bit l)
+    __shared__ unsigned s_m[K2_WARPS][K2_MAXP][K2_MAXCH + 1]; // hit mask of (particle, tile); +1: conflict-free columns
+    __shared__ unsigned short s_grp[K2_WARPS][NS][K2_MAXP + 2]; // group starts of the batch, written out row by row
+    __shared__ int s_off[K2_WARPS][NS + 1];                   // first candidate number of each stencil cell
+    __shared__ int s_start[K2_WARPS][NS];                     // first sorted index of each stencil cell
+    if (threadIdx.x == 0) s_grid = *p.d.grid;
+    __syncthreads();
+    const Grid &g = s_grid;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    const Grid &g = *p.d.grid;
+    const unsigned ltl = (1u << lane) - 1u;
     const int nwarps = gridDim.x * K2_WARPS;
     const unsigned max_ni = (unsigned)p.max_ni, ncap = (unsigned)p.ncap;
     // cells that hold owned particles: all of them, or (slab decomposition) the layers between the two halo layers
@@ -255,140 +258,142 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k_neighbours_cell(const Params 
             const int t = __shfl_up_sync(FULL, inc, o);
             if (lane >= o) inc += t;
         }
-        int total = __shfl_sync(FULL, inc, 31);
-        __syncwarp(); // the previous cell's readers of s_off / s_start are done
+        const int total = __shfl_sync(FULL, inc, 31);
+        __syncwarp(); // the previous cell's readers of the tables are done
         if (lane < NS) {
             s_off[w][lane] = inc - cn;
             s_start[w][lane] = cs;
         }
         if (lane == 0) s_off[w][NS] = total;
-        int nch = (total + 31) >> 5;
-        if (nch > K2_MAXCH) { // more candidates than any list can hold (e.g. a NaN state collapsed into one cell)
-            overflow = true;
-            nch = K2_MAXCH;
-            total = 32 * K2_MAXCH;
-        }
         __syncwarp();
         for (int b0 = 0; b0 < n_c; b0 += K2_MAXP) {
             const int nb = min(K2_MAXP, n_c - b0), i_base = s_c + b0;
-            __syncwarp(); // the previous pass has finished with s_x
-            int idi_l = 0;
+            __syncwarp(); // the previous batch has finished with s_x / s_grp
+            int idi = 0;
             if (lane < nb) {
 #pragma unroll
                 for (int k = 0; k < D; ++k) s_x[w][k][lane] = p.d.x[k][i_base + lane];
-                idi_l = p.d.id[i_base + lane];
+                idi = p.d.id[i_base + lane];
             }
-            // lane l: hits so far | owned slots so far << 11 | next stencil cell whose group start is unwritten << 22
-            unsigned cw_l = 0u;
-            // r is only counted over the first 32 particles of a cell; beyond that k_face_index searches
-            const unsigned rinc = b0 == 0 ? (1u << MLH_K2_R_SHIFT) : 0u;
+            // lane l = particle l of the batch: its list so far
+            unsigned cnt = 0u, nown = 0u, gk = 0u; // entries, owned entries, next stencil cell whose group start is unwritten
             __syncwarp();
-            for (int c0 = 0; c0 < nch; c0 += K2_U) {
-                // ---- K2_U tiles of candidates into registers ----
-                double xj[K2_U][D];
-                int jj[K2_U], idj[K2_U];
-                unsigned info[K2_U]; // mirrored stencil cell | NOPARTNER (other rank's halo) | r (or R_OVER)
-#pragma unroll
-                for (int u = 0; u < K2_U; ++u) {
-                    const int q = (c0 + u) * 32 + lane;
-                    jj[u] = -1;
-                    idj[u] = 0;
-                    info[u] = 0u;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) xj[u][k] = 1e300; // never within h of anything
-                    if (c0 + u < nch && q < total) {
+            for (int q0 = 0; q0 < total; q0 += 32 * K2_MAXCH) { // passes over the candidates (one in all but pathological cells)
+                const int npass = min(32 * K2_MAXCH, total - q0), ntile = (npass + 31) >> 5;
+                // ---- candidate tables of this pass ----
+                for (int t = 0; t < ntile; ++t) {
+                    const int ql = t * 32 + lane, q = q0 + ql;
+                    unsigned enc = 0xFFFFFFFFu;
+                    int id = 0;
+                    if (ql < npass) {
                         int k = 0; // stencil cell that holds candidate q: largest k with s_off[k] <= q
 #pragma unroll
                         for (int step = 16; step > 0; step >>= 1)
                             if (k + step < NS && s_off[w][k + step] <= q) k += step;
                         const int j = s_start[w][k] + (q - s_off[w][k]);
-                        jj[u] = j;
-                        idj[u] = p.d.id[j];
-#pragma unroll
-                        for (int k2 = 0; k2 < D; ++k2) xj[u][k2] = p.d.x[k2][j];
                         const bool offr = j < p.own_begin || j >= p.own_end;
-                        info[u] = ((unsigned)(NS - 1 - k) << MLH_K2_SC_SHIFT) | (offr ? MLH_K2_NOPARTNER : 0u) |
-                                  (b0 == 0 ? 0u : MLH_K2_R_OVER);
+                        enc = (unsigned)j | ((unsigned)(NS - 1 - k) << MLH_NNL_IDX_BITS) | (offr ? 0x80000000u : 0u);
+                        id = p.d.id[j];
                     }
+                    s_j[w][ql] = enc;
+                    s_id[w][ql] = id;
                 }
-                // ---- every particle of this pass against those tiles, ascending (so the per-lane hit counters r count
-                // the particles of the cell BELOW the current one that list the lane's candidate) ----
-                for (int l = 0; l < nb; ++l) {
-                    const unsigned i = (unsigned)(i_base + l);
-                    double xi[D];
-#pragma unroll
-                    for (int k = 0; k < D; ++k) xi[k] = s_x[w][k][l];
-                    const int idi = __shfl_sync(FULL, idi_l, l);
-                    const unsigned cw = __shfl_sync(FULL, cw_l, l);
-                    unsigned cnt = cw & 0x7ffu, nown = (cw >> 11) & 0x7ffu, gk = cw >> 22;
-                    unsigned qn = 0u; // hits of this particle in these tiles
+                __syncwarp();
+                // ---- tests: every particle of the batch against the tiles, 32 candidates per instruction; only the hit
+                // masks are kept (per particle and tile, and transposed per candidate) ----
+                for (int c0 = 0; c0 < ntile; c0 += K2_U) {
+                    double xj[K2_U][D];
+                    int jj[K2_U];
+                    unsigned col[K2_U];
 #pragma unroll
                     for (int u = 0; u < K2_U; ++u) {
-                        if (c0 + u >= nch) break; // (warp-uniform)
-                        double d[3];
+                        col[u] = 0u;
+                        jj[u] = -1;
 #pragma unroll
-                        for (int k = 0; k < D; ++k) d[k] = __dsub_rn(xj[u][k], xi[k]);
-                        const bool hit = (dist_sqr_exact<D>(d) < p.hSqr) & (jj[u] != (int)i); // Particles.cpp:341-347
-                        const unsigned m = __ballot_sync(FULL, hit);
-                        const unsigned pos = qn + __popc(m & lt);
-                        if (hit) { // list order = candidate order: the queue position IS the list slot (minus cnt)
-                            s_qj[w][pos] = jj[u];
-                            s_qi[w][pos] = info[u] | (idi < idj[u] ? 0u : 1u);
-                            info[u] += rinc;
+                        for (int k = 0; k < D; ++k) xj[u][k] = 1e300; // never within h of anything
+                        const int ql = (c0 + u) * 32 + lane;
+                        if (c0 + u < ntile && ql < npass) {
+                            jj[u] = (int)(s_j[w][ql] & MLH_NNL_IDX_MASK);
+#pragma unroll
+                            for (int k = 0; k < D; ++k) xj[u][k] = p.d.x[k][jj[u]];
                         }
-                        qn += __popc(m);
                     }
-                    __syncwarp();
-                    // ---- emit: one lane per hit ----
-                    for (unsigned base = 0; base < qn; base += 32) {
-                        const unsigned e = base + lane, slot = cnt + e;
-                        const bool valid = e < qn;
-                        const int j = valid ? s_qj[w][e] : 0;
-                        const unsigned inf = valid ? s_qi[w][e] : 0u;
-                        const bool fits = valid & (slot < max_ni);
-                        // owner = lower ORIGINAL index (Particles.cpp:1841,1889), or the only side with a list entry
-                        const bool own = fits & (!(inf & 1u) | ((inf & MLH_K2_NOPARTNER) != 0u));
-                        const unsigned mo = __ballot_sync(FULL, own);
-                        if (fits) {
-                            const unsigned at = slot * ncap + i;
-                            p.d.nnl[at] = j;
-                            p.d.fmap[at] = own ? (MLH_K2_OWNED | (inf & 1u) | ((nown + __popc(mo & lt)) << MLH_K2_RANK_SHIFT) | (inf & KEEP))
-                                               : MLH_FMAP_SKIP; // the partner owns the pair and will fill this slot
+                    for (int l = 0; l < nb; ++l) {
+                        const int i = i_base + l;
+                        double xi[D];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) xi[k] = s_x[w][k][l];
+#pragma unroll
+                        for (int u = 0; u < K2_U; ++u) {
+                            double d[3];
+#pragma unroll
+                            for (int k = 0; k < D; ++k) d[k] = __dsub_rn(xj[u][k], xi[k]);
+                            const bool hit = (dist_sqr_exact<D>(d) < p.hSqr) & (jj[u] != i); // Particles.cpp:341-347
+                            const unsigned m = __ballot_sync(FULL, hit);
+                            if (lane == 0 && c0 + u < ntile) s_m[w][l][c0 + u] = m;
+                            col[u] |= hit ? (1u << l) : 0u;
                         }
-                        if (valid & !fits) overflow = true;
-                        // group starts: the stencil cells (pk, kk] begin at this slot
-                        const unsigned kk = valid ? (unsigned)(NS - 1) - ((inf >> MLH_K2_SC_SHIFT) & 31u) : (unsigned)NS;
-                        unsigned pk = __shfl_up_sync(FULL, kk, 1);
-                        if (lane == 0) pk = gk - 1u; // (gk = 0: wraps to ~0, pk + 1 = 0)
-                        if (valid) {
-                            const unsigned short gv = (unsigned short)(slot < max_ni ? slot : max_ni);
-                            for (unsigned k = pk + 1u; k <= kk; ++k) p.d.grp[k * ncap + i] = gv;
-                        }
-                        nown += __popc(mo);
-                        const unsigned nvalid = min(32u, qn - base);
-                        gk = __shfl_sync(FULL, kk, nvalid - 1u) + 1u;
                     }
-                    cnt += qn;
-                    if (lane == l) cw_l = k2_pack(cnt, nown, gk);
-                    __syncwarp(); // the queue is reused by the next particle
+#pragma unroll
+                    for (int u = 0; u < K2_U; ++u)
+                        if (c0 + u < ntile) s_col[w][(c0 + u) * 32 + lane] = col[u];
                 }
+                __syncwarp();
+                // ---- emission: lane l walks the hit masks of particle l; every iteration emits the next hit of every
+                // particle, i.e. list slot `cnt` of consecutive particles -> one coalesced run per array ----
+                if (lane < nb) {
+                    const unsigned i = (unsigned)(i_base + lane);
+                    int t = 0;
+                    unsigned m = s_m[w][lane][0];
+                    for (;;) {
+                        while (m == 0u && ++t < ntile) m = s_m[w][lane][t];
+                        if (t >= ntile) break;
+                        const int ql = t * 32 + (__ffs(m) - 1);
+                        m &= m - 1u;
+                        const unsigned enc = s_j[w][ql];
+                        const unsigned k = (unsigned)(NS - 1) - ((enc >> MLH_NNL_IDX_BITS) & 31u);
+                        const unsigned slot = cnt++;
+                        // group starts: the stencil cells [gk, k] begin at this slot
+                        if (gk <= k) {
+                            const unsigned short gv = (unsigned short)(slot < max_ni ? slot : max_ni);
+                            do s_grp[w][gk][lane] = gv; while (++gk <= k);
+                        }
+                        if (slot < max_ni) {
+                            const bool offr = (enc >> 31) != 0u;
+                            const bool canon = idi < s_id[w][ql];
+                            // owner = lower ORIGINAL index (Particles.cpp:1841,1889), or the only side with a list entry
+                            unsigned word = MLH_FMAP_SKIP; // the partner owns the pair and will fill this slot
+                            if (canon | offr) {
+                                word = MLH_K2_OWNED | (canon ? 0u : 1u) | (nown << MLH_K2_RANK_SHIFT) |
+                                       (b0 == 0 ? ((unsigned)__popc(s_col[w][ql] & ltl) << MLH_K2_R_SHIFT) : MLH_K2_R_OVER) |
+                                       (((enc >> MLH_NNL_IDX_BITS) & 31u) << MLH_K2_SC_SHIFT) | (offr ? MLH_K2_NOPARTNER : 0u);
+                                ++nown;
+                            }
+                            const unsigned at = slot * ncap + i;
+                            p.d.nnl[at] = (int)(enc & MLH_NNL_IDX_MASK);
+                            p.d.fmap[at] = word;
+                        }
+                    }
+                }
+                __syncwarp(); // tables are rebuilt by the next pass
             }
             // ---- per particle: remaining group starts, list lengths, periodic images, owned-slot count ----
             if (lane < nb) {
                 const int i = i_base + lane;
-                const unsigned cnt_l = cw_l & 0x7ffu;
-                unsigned nown = (cw_l >> 11) & 0x7ffu;
-                if (cnt_l > max_ni) overflow = true;
-                const int nreg = (int)(cnt_l < max_ni ? cnt_l : max_ni);
-                for (unsigned k = cw_l >> 22; k < (unsigned)NS; ++k) p.d.grp[k * ncap + (unsigned)i] = (unsigned short)nreg;
+                if (cnt > max_ni) overflow = true;
+                const int nreg = (int)(cnt < max_ni ? cnt : max_ni);
+                for (; gk < (unsigned)NS; ++gk) s_grp[w][gk][lane] = (unsigned short)nreg;
                 p.d.noi[i] = nreg;
                 int ng = 0;
-                if (PER) ng = ghost_entries<D>(p, i, c, nreg, &nown, &overflow);
+                if (PER) ng = ghost_entries<D>(p, g, i, c, nreg, &nown, &overflow);
                 p.d.noig[i] = ng;
                 p.d.nown[i] = (int)nown;
                 const unsigned len = (unsigned)(nreg + ng);
                 maxlen = len > maxlen ? len : maxlen;
             }
+            __syncwarp();
+            for (int k = 0; k < NS; ++k)
+                if (lane < nb) p.d.grp[(unsigned)k * ncap + (unsigned)(i_base + lane)] = s_grp[w][k][lane];
         }
     }
     if (overflow) atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);

@@ -136,20 +136,14 @@ __global__ void __launch_bounds__(128) k_density_matrix(const Params p) {
         if (s + 2 < nreg) e_next2 = p.d.nnl[(size_t)(s + 2) * p.ncap + i];
         if (s + 1 < nreg) neighbour_position<D>(p, e_next, xn);
         neighbour_geometry_from<D, false>(p, xi, e, xc, d, &r);
-        const double W = cubic_spline(r, p);
-        p.d.wc[(size_t)s * p.ncap + i] = W; // kept for the matrix sweep and K3b (W, then psi) ..
-        p.d.rc[(size_t)s * p.ncap + i] = r; // .. and for K3b's signal velocity
-        omg = __dadd_rn(omg, W);
+        omg = __dadd_rn(omg, cubic_spline(r, p));
     }
     omg = __dadd_rn(omg, cubic_spline(0., p));
     if (PER)
         for (int s = nreg; s < ntot; ++s) {
             double d[3], r;
             neighbour_geometry<D, true>(p, xi, p.d.nnl[(size_t)s * p.ncap + i], d, &r);
-            const double W = cubic_spline(r, p);
-            p.d.wc[(size_t)s * p.ncap + i] = W;
-            p.d.rc[(size_t)s * p.ncap + i] = r;
-            omg = __dadd_rn(omg, W);
+            omg = __dadd_rn(omg, cubic_spline(r, p));
         }
     const double rho = __dmul_rn(p.d.m[i], omg);
     const double P = __dmul_rn(__dmul_rn(__dsub_rn(p.gamma, 1.), rho), p.d.u[i]);
@@ -178,27 +172,16 @@ __global__ void __launch_bounds__(128) k_density_matrix(const Params p) {
     e_next = ntot > 0 ? p.d.nnl[i] : 0;
     e_next2 = ntot > 1 ? p.d.nnl[(size_t)p.ncap + i] : 0;
     if (ntot > 0) neighbour_position<D>(p, e_next, xn);
-    double w_next = ntot > 0 ? p.d.wc[i] : 0.; // the kernel value of the first sweep (same bits), read a visit ahead
 #pragma unroll 2
     for (int s = 0; s < ntot; ++s) {
-        double d[3];
+        double d[3], r;
         const int e = e_next;
         const double xc[3] = {xn[0], xn[1], xn[2]};
-        const double W = w_next;
         e_next = e_next2;
         if (s + 2 < ntot) e_next2 = p.d.nnl[(size_t)(s + 2) * p.ncap + i];
-        if (s + 1 < ntot) {
-            neighbour_position<D>(p, e_next, xn);
-            w_next = p.d.wc[(size_t)(s + 1) * p.ncap + i];
-        }
-#pragma unroll
-        for (int k = 0; k < D; ++k) { // xj - xi (Particles.cpp:1208-1210; ghosts :2318-2320)
-            double xj = xc[k];
-            if (PER) xj = image_coord(xj, (e >> (MLH_NNL_IDX_BITS + 2 * k)) & 3, p.grid.bmin[k], p.grid.bmax[k]);
-            d[k] = __dsub_rn(xj, xi[k]);
-        }
-        const double psij = __ddiv_rn(W, omg);
-        p.d.wc[(size_t)s * p.ncap + i] = psij; // psi_j(x_i) for K3b
+        if (s + 1 < ntot) neighbour_position<D>(p, e_next, xn);
+        neighbour_geometry_from<D, PER>(p, xi, e, xc, d, &r);
+        double psij = __ddiv_rn(cubic_spline(r, p), omg);
 #pragma unroll
         for (int a = 0; a < D; ++a)
 #pragma unroll

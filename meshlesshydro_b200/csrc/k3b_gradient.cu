@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(128, MLH_K3B_BLOCKS(D)) k_gradient_limit(const
         for (int f = 0; f < NF; ++f) fi[f] = own[fidx[f]];
 #pragma unroll
         for (int k = 0; k < D * D; ++k) B[k] = p.d.B[k][i];
+        const double omg = own[2 * D + 3];
         const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
 
         double g[NF][D];
@@ -84,28 +85,22 @@ __global__ void __launch_bounds__(128, MLH_K3B_BLOCKS(D)) k_gradient_limit(const
         double nbn[PK1];
         int e_next2 = ntot > 1 ? p.d.nnl[(size_t)p.ncap + i] : 0;
         if (ntot > 0) load_neighbour<D, PER>(p, e_next, nbn);
-        // psi_j(x_i) = W(r_ij)/omega_i and r_ij come from K3's per-slot cache (the bits K3 computed: Particles.cpp:1170-1175,
-        // 1213 / ghosts :2275-2280, 2323), read one visit ahead
-        double psi_next = ntot > 0 ? p.d.wc[i] : 0., r_next = ntot > 0 ? p.d.rc[i] : 0.;
 #pragma unroll 2
         for (int s = 0; s < ntot; ++s) {
             double nb[PK1];
 #pragma unroll
             for (int k = 0; k < PK1; ++k) nb[k] = nbn[k];
-            const double psij = psi_next, r = r_next;
             e_next = e_next2;
             if (s + 2 < ntot) e_next2 = p.d.nnl[(size_t)(s + 2) * p.ncap + i];
-            if (s + 1 < ntot) {
-                load_neighbour<D, PER>(p, e_next, nbn);
-                psi_next = p.d.wc[(size_t)(s + 1) * p.ncap + i];
-                r_next = p.d.rc[(size_t)(s + 1) * p.ncap + i];
-            }
+            if (s + 1 < ntot) load_neighbour<D, PER>(p, e_next, nbn);
             double d[3], sd[3];
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 d[k] = __dsub_rn(nb[k], xi[k]);
                 sd[k] = __dsub_rn(xi[k], nb[k]);
             }
+            const double r = sqrt(dist_sqr_exact<D>(sd)); // Particles.cpp:1170-1175 / :2275-2280
+            const double psij = __ddiv_rn(cubic_spline(r, p), omg);
             double pt[D];
 #pragma unroll
             for (int a = 0; a < D; ++a) {

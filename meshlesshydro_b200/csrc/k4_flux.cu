@@ -520,20 +520,14 @@ template <int D> struct FaceFrame {
     double L[D == 2 ? 2 : 9]; // 2D: (ax, ay) of [[ax, ay], [-ay, ax]]; 3D: row-major Rodrigues matrix
 };
 template <int D>
-__device__ __forceinline__ void face_rotate(const double *A, double *Wa, double *Wb, FaceFrame<D> &fr) {
+__device__ __forceinline__ void face_frame(const double *A, FaceFrame<D> &fr) {
     double n2 = 0.;
 #pragma unroll
     for (int k = 0; k < D; ++k) n2 += A[k] * A[k];
     const double inv = 1. / sqrt(n2);
     if (D == 2) {
-        const double L0 = inv * A[0], L1 = inv * A[1];
-        fr.L[0] = L0;
-        fr.L[1] = L1;
-        const double bR0 = Wb[2], bR1 = Wb[3], bL0 = Wa[2], bL1 = Wa[3];
-        Wb[2] = L0 * bR0 + L1 * bR1;
-        Wb[3] = -L1 * bR0 + L0 * bR1;
-        Wa[2] = L0 * bL0 + L1 * bL1;
-        Wa[3] = -L1 * bL0 + L0 * bL1;
+        fr.L[0] = inv * A[0];
+        fr.L[1] = inv * A[1];
     } else {
         // rotationMatrix3D(a = hatA, b = unitX): v = a x b = (0, a2, -a1), Rodrigues with n = 1/(1+cos)
         // (singular for hatA = -x, as the reference); rotationMatrix3D(unitX, hatA) is its transpose
@@ -550,6 +544,20 @@ __device__ __forceinline__ void face_rotate(const double *A, double *Wa, double 
         L[6] = -v1;
         L[7] = n * v1 * v2;
         L[8] = 1. - n * (v1 * v1);
+    }
+}
+template <int D>
+__device__ __forceinline__ void face_rotate(const double *A, double *Wa, double *Wb, FaceFrame<D> &fr) {
+    face_frame<D>(A, fr);
+    if (D == 2) {
+        const double L0 = fr.L[0], L1 = fr.L[1];
+        const double bR0 = Wb[2], bR1 = Wb[3], bL0 = Wa[2], bL1 = Wa[3];
+        Wb[2] = L0 * bR0 + L1 * bR1;
+        Wb[3] = -L1 * bR0 + L0 * bR1;
+        Wa[2] = L0 * bL0 + L1 * bL1;
+        Wa[3] = -L1 * bL0 + L0 * bL1;
+    } else {
+        const double *L = fr.L;
         const double bR[3] = {Wb[2], Wb[3], Wb[D + 1]}, bL[3] = {Wa[2], Wa[3], Wa[D + 1]};
         Wb[2] = L[0] * bR[0] + L[1] * bR[1] + L[2] * bR[2];
         Wb[3] = L[3] * bR[0] + L[4] * bR[1] + L[5] * bR[2];
@@ -628,12 +636,39 @@ __device__ __forceinline__ double select_dt(const Params &p, double dt_fixed, do
 // W component nu -> gradient field slot: W = [rho, P, vx, vy, vz], slots rho 0, vx 1, vy 2, vz 3, P 4
 __device__ __forceinline__ int w2f(int nu) { return nu == 0 ? 0 : (nu == 1 ? 4 : nu - 1); }
 
-// staging record of one face: Wa[NW], Wb[NW], vF[D], A[D] -> 4D+4 doubles, field-major (field k of face f of the
-// chunk at stage[k * cstride + f]) so that both K4a's stores and K4b's loads are coalesced
+// staging record of one face, written by K4a with the velocities ALREADY ROTATED into the face frame (Riemann::Riemann,
+// Riemann.cpp:19-81): the six fields of the one-dimensional Riemann problem come first, so the solver setup reads only
+// those; the finish kernel reads everything.  4D+4 doubles, field-major (field k of face f of the chunk at
+// stage[k * cstride + f]) so that K4a's stores and K4b's loads are coalesced.
+//   [0..5] rhoL PL uL rhoR PR uR   (L = canonical endpoint a, u = velocity along the face normal)
+//   [6..]  transverse velocities of a (D-1), of b (D-1), vFrame (D), A_ij (D)
 template <int D> struct FaceRec {
     static constexpr int NW = D + 2;
-    static constexpr int WA = 0, WB = NW, VF = 2 * NW, AA = 2 * NW + D, NREC = 2 * NW + 2 * D;
+    static constexpr int RHOL = 0, PL = 1, UL = 2, RHOR = 3, PR = 4, UR = 5, VTA = 6, VTB = 6 + (D - 1), VF = 6 + 2 * (D - 1),
+                         AA = 6 + 2 * (D - 1) + D, NREC = 2 * NW + 2 * D;
+    // layout of the debug record (mlh_debug_fetch "face_rec": un-rotated, the reference's per-slot arrays)
+    static constexpr int DBG_WA = 0, DBG_WB = NW, DBG_VF = 2 * NW, DBG_AA = 2 * NW + D;
 };
+template <int D>
+__device__ __forceinline__ void face_store(double *rec, size_t fs, const double *Wa, const double *Wb, const double *vF, const double *A) {
+    using R = FaceRec<D>;
+    rec[R::RHOL * fs] = Wa[0];
+    rec[R::PL * fs] = Wa[1];
+    rec[R::UL * fs] = Wa[2];
+    rec[R::RHOR * fs] = Wb[0];
+    rec[R::PR * fs] = Wb[1];
+    rec[R::UR * fs] = Wb[2];
+#pragma unroll
+    for (int k = 1; k < D; ++k) {
+        rec[(R::VTA + k - 1) * fs] = Wa[2 + k];
+        rec[(R::VTB + k - 1) * fs] = Wb[2 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        rec[(R::VF + k) * fs] = vF[k];
+        rec[(R::AA + k) * fs] = A[k];
+    }
+}
 
 #define MLH_FACE_TILE 128
 
@@ -649,14 +684,22 @@ template <int D> struct FaceRec {
 // member mask, list length and face base of its partner -- five dependent gathers, 0.10 ms at 61^3,
 // profiles/r02_k_face_index_ncu_full.txt; a search of the partner's list cost 0.27-0.42 ms, profiles/r01h.]
 // Periodic-image slots (few) and cells of more than 32 particles find the partner's slot by scanning its list.
+#define MLH_FI_STAGE 4096 // faces staged per block (32 KB): 128 particles x ~16 (3D) .. ~24 (2D) owned slots
 template <bool PER>
 __global__ void __launch_bounds__(128) k_face_index(const Params p) {
-    const int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.own_end) return;
-    const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
-    const int fs = p.d.face_start[i];
+    // The faces of a block's 128 consecutive particles are one contiguous range of the face list: (owner, entry) pairs
+    // are collected in shared memory and leave as full lines, instead of two 4-byte stores per face scattered over as
+    // many sectors (k_face_index was LSU-queue bound on them: lg_throttle 19.6, profiles/r2c_k_face_index_scatter_*).
+    __shared__ int s_fa[MLH_FI_STAGE], s_fe[MLH_FI_STAGE];
+    const int i0 = p.own_begin + blockIdx.x * blockDim.x;
+    const int i = i0 + threadIdx.x;
+    const int ilast = min(i0 + (int)blockDim.x, p.own_end); // one past the block's last particle
+    const int fbase = p.d.face_start[i0], fend = min(p.d.face_start[ilast], p.fcap);
     const int max_ni = p.max_ni;
     bool over = false;
+    if (i < p.own_end) {
+    const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
+    const int fs = p.d.face_start[i];
     for (int s0 = 0; s0 < ntot; s0 += 4) {
         unsigned v[4], g0[4];
         int e[4];
@@ -686,8 +729,14 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
                 p.d.fmap[at] = MLH_FMAP_SKIP;
                 continue;
             }
-            p.d.fa[f] = i | (int)(sign << 31); // bit 31: the partner is the canonical endpoint (lower original index)
-            p.d.fe[f] = e[q];
+            const int fav = i | (int)(sign << 31); // bit 31: the partner is the canonical endpoint (lower original index)
+            if (f - fbase < MLH_FI_STAGE) {
+                s_fa[f - fbase] = fav;
+                s_fe[f - fbase] = e[q];
+            } else { // more faces in this block than the stage holds
+                p.d.fa[f] = fav;
+                p.d.fe[f] = e[q];
+            }
             p.d.fmap[at] = ((unsigned)f << 2) | MLH_K2_OWNED | sign;
             if (v[q] & MLH_K2_NOPARTNER) continue;
             const int j = e[q] & MLH_NNL_IDX_MASK;
@@ -714,6 +763,13 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
             if (t >= 0) p.d.fmap[(size_t)t * p.ncap + j] = ((unsigned)f << 2) | 1u; // the partner adds -F
         }
     }
+    }
+    __syncthreads();
+    const int nst = min(fend - fbase, MLH_FI_STAGE);
+    for (int k = threadIdx.x; k < nst; k += blockDim.x) {
+        p.d.fa[fbase + k] = s_fa[k];
+        p.d.fe[fbase + k] = s_fe[k];
+    }
     if (over) atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);
 }
 
@@ -721,10 +777,16 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
 template <int D>
 __device__ __forceinline__ void face_load(const double *rec, size_t fs, double *Wa, double *Wb, double *vF, double *A) {
     using R = FaceRec<D>;
+    Wa[0] = rec[R::RHOL * fs];
+    Wa[1] = rec[R::PL * fs];
+    Wa[2] = rec[R::UL * fs];
+    Wb[0] = rec[R::RHOR * fs];
+    Wb[1] = rec[R::PR * fs];
+    Wb[2] = rec[R::UR * fs];
 #pragma unroll
-    for (int nu = 0; nu < D + 2; ++nu) {
-        Wa[nu] = rec[(R::WA + nu) * fs];
-        Wb[nu] = rec[(R::WB + nu) * fs];
+    for (int k = 1; k < D; ++k) {
+        Wa[2 + k] = rec[(R::VTA + k - 1) * fs];
+        Wb[2 + k] = rec[(R::VTB + k - 1) * fs];
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -745,12 +807,12 @@ __host__ __device__ __forceinline__ int q_region_cap(int cstride) { // faces per
     const int nwt = (cstride + 31) / 32;
     return (nwt + MLH_Q_REGIONS - 1) / MLH_Q_REGIONS * 32;
 }
-// Riemann::Riemann + the start of RiemannSolver::solve for one face (body of k_face_setup, also the tail of the fused
-// k_face_states): rotate into the face frame, sound speeds, vacuum test, initial guess, f(0), f(guess).  Faces that
-// need no iteration get P* at once, the others are appended to the solver queue.  The whole warp must call it (ballots);
-// Wa / Wb are rotated in place.
-template <int D>
-__device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid, int fl, double *Wa, double *Wb, const double *A,
+// The start of RiemannSolver::solve for one face (body of k_face_setup, also the tail of the fused k_face_states):
+// sound speeds, vacuum test, initial guess, f(0), f(guess) of the one-dimensional problem in the face frame.  Faces
+// that need no iteration get P* at once, the others are appended to the solver queue.  The whole warp must call it
+// (ballots).
+__device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid, int fl, double rhoL, double PL, double uL,
+                                                     double rhoR, double PR, double uR,
                                                      double *__restrict__ pstar, double *__restrict__ qd, int *__restrict__ qi,
                                                      int *__restrict__ qcount, int rcap) {
     const int lane = threadIdx.x & 31;
@@ -758,10 +820,8 @@ __device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid
     RsProblem q;
     RsIter it;
     if (valid) {
-        FaceFrame<D> fr;
-        face_rotate<D>(A, Wa, Wb, fr);
         // left = canonical particle a, right = b, along +A (Riemann.cpp:93-94)
-        if (rs_setup(p.rs, Wa[0], Wa[2], Wa[1], Wb[0], Wb[2], Wb[1], q)) {
+        if (rs_setup(p.rs, rhoL, uL, PL, rhoR, uR, PR, q)) {
             rs_iter_begin(q, it);
             method = it.method;
             if (method == RS_DONE) pstar[fl] = it.b;
@@ -1042,30 +1102,25 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_fac
             double *dbg = p.d.dbg_face + (size_t)f * R::NREC;
 #pragma unroll
             for (int nu = 0; nu < NW; ++nu) {
-                dbg[R::WA + nu] = Wa[nu];
-                dbg[R::WB + nu] = Wb[nu];
+                dbg[R::DBG_WA + nu] = Wa[nu];
+                dbg[R::DBG_WB + nu] = Wb[nu];
             }
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-                dbg[R::VF + k] = vF[k];
-                dbg[R::AA + k] = A[k];
+                dbg[R::DBG_VF + k] = vF[k];
+                dbg[R::DBG_AA + k] = A[k];
             }
         }
+        // ---- Riemann::Riemann (Riemann.cpp:7-81): velocities into the face frame, once, here -- the solver setup then
+        // reads 6 of the record's 4D+4 fields and the finish kernel does not rotate again ----
+        {
+            FaceFrame<D> fr;
+            face_rotate<D>(A, Wa, Wb, fr);
+        }
         // ---- stage the record (field-major inside the chunk: coalesced here and in K4b) ----
-        double *rec = stage + (f - f0);
-        const size_t fs = (size_t)cstride; // field stride
-#pragma unroll
-        for (int nu = 0; nu < NW; ++nu) {
-            rec[(R::WA + nu) * fs] = Wa[nu];
-            rec[(R::WB + nu) * fs] = Wb[nu];
-        }
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            rec[(R::VF + k) * fs] = vF[k];
-            rec[(R::AA + k) * fs] = A[k];
-        }
+        face_store<D>(stage + (f - f0), (size_t)cstride, Wa, Wb, vF, A);
         } // valid
-        if (FUSE) face_setup_and_queue<D>(p, valid, fl, Wa, Wb, A, pstar, qd, qi, qcount, rcap);
+        if (FUSE) face_setup_and_queue(p, valid, fl, Wa[0], Wa[1], Wa[2], Wb[0], Wb[1], Wb[2], pstar, qd, qi, qcount, rcap);
     }
 }
 
@@ -1094,17 +1149,21 @@ template <int D>
 __global__ void __launch_bounds__(MLH_FACE_TILE, 8) k_face_setup(const Params p, const double *__restrict__ stage, double *__restrict__ pstar,
                                                               double *__restrict__ qd, int *__restrict__ qi, int *__restrict__ qcount,
                                                               int f0, int cstride) {
-    constexpr int NW = D + 2;
     const int nfaces = min(p.d.face_start[p.own_end], p.fcap);
     const int f1 = min(nfaces, f0 + cstride);
     const size_t fs = (size_t)cstride;
     const int nround = (f1 - f0 + 31) / 32 * 32; // whole warps stay in the loop (ballots in face_setup_and_queue)
     const int rcap = q_region_cap(cstride);
+    using R = FaceRec<D>;
     for (int fl = blockIdx.x * MLH_FACE_TILE + threadIdx.x; fl < nround; fl += gridDim.x * MLH_FACE_TILE) {
         const bool valid = f0 + fl < f1;
-        double Wa[NW], Wb[NW], vF[D], A[D];
-        if (valid) face_load<D>(stage + fl, fs, Wa, Wb, vF, A);
-        face_setup_and_queue<D>(p, valid, fl, Wa, Wb, A, pstar, qd, qi, qcount, rcap);
+        double w[6] = {1., 1., 0., 1., 1., 0.};
+        if (valid) {
+            const double *rec = stage + fl;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) w[k] = rec[k * fs];
+        }
+        face_setup_and_queue(p, valid, fl, w[R::RHOL], w[R::PL], w[R::UL], w[R::RHOR], w[R::PR], w[R::UR], pstar, qd, qi, qcount, rcap);
     }
 }
 
@@ -1249,8 +1308,8 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_FINISH_BLOCKS) k_face_finis
     for (int f = f0 + blockIdx.x * MLH_FACE_TILE + threadIdx.x; f < f1; f += gridDim.x * MLH_FACE_TILE) {
         double Wa[NW], Wb[NW], vF[D], A[D], F[NW];
         FaceFrame<D> fr;
-        face_load<D>(stage + (f - f0), fs, Wa, Wb, vF, A);
-        face_rotate<D>(A, Wa, Wb, fr);
+        face_load<D>(stage + (f - f0), fs, Wa, Wb, vF, A); // velocities already in the face frame (K4a)
+        face_frame<D>(A, fr);
         const double Ps = pstar[f - f0];
         double rhoSol, uSol, PSol;
         int flag;
@@ -1516,15 +1575,18 @@ __global__ void k_pack_faces(const double *__restrict__ WL, const double *__rest
     constexpr int NW = D + 2;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
-    const size_t fs = (size_t)cstride;
+    double Wa[NW], Wb[NW], v[D], a[D];
     for (int nu = 0; nu < NW; ++nu) {
-        stage[(R::WA + nu) * fs + f] = WL[(size_t)f * NW + nu];
-        stage[(R::WB + nu) * fs + f] = WR[(size_t)f * NW + nu];
+        Wa[nu] = WL[(size_t)f * NW + nu];
+        Wb[nu] = WR[(size_t)f * NW + nu];
     }
     for (int k = 0; k < D; ++k) {
-        stage[(R::VF + k) * fs + f] = vF[(size_t)f * D + k];
-        stage[(R::AA + k) * fs + f] = A[(size_t)f * D + k];
+        v[k] = vF[(size_t)f * D + k];
+        a[k] = A[(size_t)f * D + k];
     }
+    FaceFrame<D> fr;
+    face_rotate<D>(a, Wa, Wb, fr); // Riemann::Riemann, as K4a does for the faces of a step
+    face_store<D>(stage + f, (size_t)cstride, Wa, Wb, v, a);
 }
 template <int D>
 __global__ void k_unpack_fluxes(const double *__restrict__ F, double *__restrict__ out, int n) {

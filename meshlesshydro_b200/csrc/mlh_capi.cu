@@ -87,8 +87,6 @@ static void carve_pool(mlh_ctx *c, Carver &cv) {
     d.ckey = cv.take<int>(n); d.crank = cv.take<int>(n); d.perm = cv.take<int>(n);
     d.nnl = cv.take<int>(n * (size_t)p.max_ni);
     d.fmap = cv.take<unsigned>(n * (size_t)p.max_ni);
-    d.wc = cv.take<double>(n * (size_t)p.max_ni);
-    d.rc = cv.take<double>(n * (size_t)p.max_ni);
     d.grp = cv.take<unsigned short>(n * (size_t)27);
     d.nown = cv.take<int>(n);
     d.face_start = cv.take<int>(n + 1);

@@ -79,10 +79,6 @@ struct DevPtrs {
     //   pk1[i*PK1 ..] = x[D], v[D], rho, P, cs, omega          (written by K3;  PK1 = 2D+4)
     //   pk2[i*PK2 ..] = Binv[D*D] row-major, grad[(D+2)][D] in W order rho,P,vx,vy(,vz)   (written by K3b; PK2 = D*D+(D+2)*D)
     double *pk1, *pk2;
-    // per-slot cache (slot-major like nnl, coalesced for the thread-per-particle sweeps): K3's first sweep stores the
-    // kernel value W(r_ij) and r_ij of every list entry, its second sweep turns W into psi_j(x_i) = W / omega_i, K3b
-    // reads both -- instead of redoing sqrt + division + spline (+ division) per visit in three more sweeps
-    double *wc, *rc;
     // CUR set
     double *cx[3], *cv[3], *cm, *cu;
     int *cid;
