@@ -5,10 +5,18 @@
 
 A "step" is one full pass of the hot path (MeshlessScheme::run loop body, phases 1-16: cell sort ->
 neighbour search -> density/matrices -> gradients/limiter/CFL -> faces + exact Riemann -> update) over
-all particles of the workload.  N=1 default workload = BASELINE.json configs[1]: Sedov blast 3D,
-N = 61^3 (synthetic jittered lattice of that shape, seed 6102003; SEAGen/HDF5 are not available).
-N>1: the domain is slab-decomposed (NCCL halo exchange + allreduce-min of dt); weak scaling, the box
-grows to n_side = round(61 * N^(1/3)) so every GPU keeps ~61^3 particles.
+all particles of the workload.  Default workload at EVERY N = BASELINE.json configs[3]: Kelvin-Helmholtz
+2D MFV, N = 2000^2 = 4 M particles (the largest configuration that BASELINE lists for one GPU, "at
+1/2/4/8 B200"); with N>1 the same 4 M particles are slab-decomposed over the GPUs (NCCL halo exchange +
+allreduce-min of dt) -> STRONG scaling.  `--workload sedov61` = configs[1] (Sedov 3D 61^3; with N>1 weak
+scaling, ~61^3 per GPU), `--workload sedov256` = configs[4].  At N=8 the default run appends the
+Sedov 256^3 numbers (configs[4]) under "also" unless --no-also is given.  Initial conditions are synthetic
+(jittered lattices of those shapes, seed 6102003; SEAGen/HDF5 files are not available).
+
+The timed region is made at least 0.5 s long (so that the 100 ms clock sampler covers it): the block of
+--steps steps is repeated `timed_region.blocks` times back to back inside ONE region, ms_per_step is the
+mean over all of them.  With N>1 rank 0 also runs a small case sharded and on one GPU and reports
+whether the results agree bit for bit ("mgpu_check").
 
 One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events on the library's
 stream), `e2e` = the same metric through the C ABI with HOST (pinned) buffers: upload + step + download
@@ -116,17 +124,21 @@ def time_reference(ic_factory, preset, n_side, steps, warmup, budget_s):
     from cpu_oracles import Reference, Oracle, make_config
     from meshlesshydro_b200 import ic as IC
     variant = _ref_variant(preset)
-    gen = {"sedov3d": IC.sedov, "kh2d": lambda n: IC.kelvin_helmholtz(n, lattice=False),
+    gen = {"sedov3d": IC.sedov, "kh2d": lambda n: IC.kelvin_helmholtz(n, lattice=True, jitter=0.2),
            "fb2d": lambda n: IC.fluid_block(n, jitter=0.05)}[preset]
     dim = 3 if preset == "sedov3d" else 2
-    per_particle_s = 3.2e-5 if dim == 3 else 4e-5  # first guess, refined by the first warm-up step
+
+    def per_particle_s(side):
+        # measured in this image (one core): 3D 3.2e-5 s; 2D 4.0e-5 s, plus the reference's brute-force ghost search
+        # (Particles::ghostNNS, O(N N_ghost)) in periodic runs: 4.4e-5 at side 150, 5.1e-5 at side 300
+        return 3.2e-5 if dim == 3 else (4.0e-5 + 3.6e-8 * side if preset == "kh2d" else 4.0e-5)
     kind = "reference" if Reference.available(variant) else "port"
     while True:
         n = n_side ** dim
-        est = per_particle_s * n * (steps + warmup)
+        est = per_particle_s(n_side) * n * (steps + warmup)
         if est <= budget_s or n_side <= 16:
             break
-        n_side = max(16, int(n_side * (budget_s / est) ** (1.0 / dim)))
+        n_side = max(16, min(n_side - 1, int(n_side * (budget_s / est) ** (1.0 / dim))))
     ic = gen(n_side)
     n = len(ic["x"])
     if kind == "reference":
@@ -150,57 +162,60 @@ def time_reference(ic_factory, preset, n_side, steps, warmup, budget_s):
 
 
 # ------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=None)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.warmup < 3 and args.impl == "b200":
-        args.warmup = 3
-    wl = workloads()
-    wname = args.workload or "sedov61"
-    factory, preset, wdesc = wl[wname]
+SIDES = {"sedov61": 61, "sedov128": 128, "sedov256": 256, "kh100": 100, "kh1000": 1000, "kh2000": 2000, "fb1000": 1000}
+CPU_SIDES = {"sedov61": 61, "sedov128": 61, "sedov256": 61, "kh100": 100, "kh1000": 200, "kh2000": 200, "fb1000": 200}
+
+
+def mgpu_bitwise_check(dist, local_rank, rank, world):
+    """A small periodic case run sharded over all ranks and, on rank 0, on one GPU: states and time steps must agree
+    bit for bit (same neighbour order, same arithmetic; cut faces are evaluated identically on both ranks)."""
+    from meshlesshydro_b200 import capi, multigpu, ic as IC
+    ic = IC.kelvin_helmholtz(max(128, 32 * world), lattice=True, jitter=0.2)
+    steps = 3
+
+    def cfg_():
+        c = capi.make_config("kh2d", ic["h"], ic["gamma"], ic.get("box"), abs_mode=capi.ABS_INT_TRUNC, max_interactions=96)
+        c.device = local_rank
+        return c
+    gpu, _ = multigpu.create_sharded(cfg_(), ic, dist)
+    dts = [gpu.step() for _ in range(steps)]
+    st = gpu.download_state()
+    flags = gpu.error_flags()
+    gpu.close()
+    names = ["x", "y", "vx", "vy", "m", "u"]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {k: st[k] for k in names + ["ids"]})
+    res = None
+    if rank == 0:
+        N = len(ic["x"])
+        full = {k: np.full(N, np.nan) for k in names}
+        count = np.zeros(N, dtype=np.int64)
+        for part in gathered:
+            count[part["ids"]] += 1
+            for k in names:
+                full[k][part["ids"]] = part[k]
+        one = capi.MfvGpu(cfg_())
+        one.upload(ic)
+        dts1 = [one.step() for _ in range(steps)]
+        ref = one.download_state()
+        one.close()
+        equal = bool(np.all(count == 1)) and dts == dts1 and all(np.array_equal(full[k], ref[k]) for k in names)
+        res = {"case": "KH 2D N=%d periodic, %d steps, %d slabs vs 1 GPU" % (N, steps, world), "bitwise_equal": equal,
+               "ownership_is_partition": bool(np.all(count == 1)), "device_flags": flags}
+    return res
+
+
+def run_workload(args, wname, dist, rank, world, local_rank, want_profile=True, want_e2e=True):
+    """Time one workload on `world` GPUs.  Returns the measurement dict (rank 0) or None."""
+    import torch
+    from meshlesshydro_b200 import capi
+    factory, preset, wdesc = workloads()[wname]
+    scaling = "strong"
     n_side_weak = None
     if world > 1 and wname == "sedov61":
+        scaling = "weak"
         n_side_weak = int(round(61 * world ** (1.0 / 3.0)))
         wdesc = "Sedov blast 3D MFV, weak scaling: N=%d^3 over %d slabs (~61^3 per GPU)" % (n_side_weak, world)
-
-    # ---------------- reference arm ----------------
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        side = {"sedov61": 61, "sedov128": 128, "sedov256": 256, "kh100": 100, "kh1000": 1000, "kh2000": 2000, "fb1000": 1000}[wname]
-        res = time_reference(factory, preset, n_side_weak or side, max(1, args.steps), max(0, min(args.warmup, 1)), budget_s=150.0)
-        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wdesc, "n_particles_sample": res["n_particles"]},
-                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
-        return 0
-
-    # ---------------- B200 arm ----------------
-    # exactly ONE line may reach stdout; libraries (NCCL prints its version banner there) are sent to stderr
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
-    import torch
-    import torch.distributed as dist
-    from meshlesshydro_b200 import capi
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the MFV path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ic = factory(n_side_weak) if n_side_weak else factory()
     D = ic["dim"]
     n_total = len(ic["x"])
@@ -232,9 +247,18 @@ def main():
         return float(t.item())
 
     # ---- device-resident throughput ----
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup - 2, 1)):
         gpu.step(want_dt=False)
     barrier()
+    gpu.timer_start()
+    for _ in range(2):  # the last two warm-up steps also size the timed region
+        gpu.step(want_dt=False)
+    est_ms = max_over_ranks(gpu.timer_stop()) / 2.0
+    blocks = max(1, int(np.ceil(600.0 / max(est_ms * args.steps, 1e-3))))  # >= 0.6 s of steps in the region
+    if world > 1:
+        t = torch.tensor([blocks], dtype=torch.int64, device="cuda")
+        dist.broadcast(t, src=0)
+        blocks = int(t.item())
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -242,99 +266,35 @@ def main():
     l0 = gpu.launch_count()
     barrier()
     gpu.timer_start()
-    for _ in range(args.steps):
+    for _ in range(args.steps * blocks):
         gpu.step(want_dt=False)
     ms = gpu.timer_stop()
     barrier()
-    launches = gpu.launch_count() - l0
+    launches = (gpu.launch_count() - l0) / blocks
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
     flags = gpu.error_flags()
-    value = n_total * args.steps / (ms * 1e-3)
+    nsteps = args.steps * blocks
+    value = n_total * nsteps / (ms * 1e-3)
+    res = {"wname": wname, "wdesc": wdesc, "scaling": scaling, "D": D, "n_total": n_total, "n_local": n_local, "value": value,
+           "ms_per_step": ms / nsteps, "timed_region": {"blocks": blocks, "steps_total": nsteps, "seconds": ms * 1e-3},
+           "launches": launches, "clocks": clocks, "flags": flags, "h": ic["h"]}
 
     # ---- per-kernel profile (separate, untimed pass) for the roofline object ----
-    gpu.profile(True)
-    psteps = max(3, min(args.steps, 10))
-    for _ in range(psteps):
-        gpu.step(want_dt=False)
-    prof = gpu.profile_read()
-    gpu.profile(False)
-    noi_mean = float((gpu.fetch("noi").mean() + gpu.fetch("noiGhosts").mean()))  # rank 0's particles when sharded
-    nfaces = int(gpu.fetch("num_faces")[0])
-    # per STEP (a kernel of the face-chunk loop may launch more than once per step; launches beyond the last face are empty)
-    per_launch = {k: v[0] / psteps for k, v in prof.items() if v[1]}
-    step_ms_prof = sum(v[0] for v in prof.values()) / psteps
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_src = "of measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "of fallback (B200_PROFILING.md 6.65 TB/s)"
-    fp64_peak = capi.fp64_peak_tflops(local_rank)
-    ops = {}
-    try:
-        ops = json.load(open(os.path.join(ROOT, "profiles", "fp64_ops.json"))).get(wname, {})
-    except Exception:
-        pass
-    # ---- roofline of the dominant kernel ----
-    top = max(per_launch.items(), key=lambda kv: prof[kv[0]][0])[0]
-    top_ms = per_launch[top]
-    nslots = n_local * noi_mean if noi_mean else None
-    frec = 4 if D == 2 else 6
-    hbm_models = {  # algorithmic bytes per launch
-        "k4a_face_states": lambda: n_local * (2 * D + 4 + D * D + (D + 2) * D) * 8 + nfaces * ((4 * D + 4) * 8 + 8),
-        "k4c_flux_sum_update": lambda: nslots * (4 + frec * 8) + n_local * 2 * (2 * D + 2) * 8,
-        "k2b_face_index": lambda: nslots * 12 + nfaces * 8,
-        "k1_gather": lambda: n_local * 2 * ((2 * D + 2) * 8 + 8),
-    }
-    roofline = {"kernel": top, "share_of_step": prof[top][0] / psteps / step_ms_prof if step_ms_prof else None,
-                "ms_per_step": top_ms, "launches_per_step": prof[top][1] / psteps, "traffic": None}
-    kops = ops.get(top)
-    if kops:
-        roofline["traffic"] = kops.get("dram_bytes")
-    if top in hbm_models and (nfaces is not None):
-        ab = float(hbm_models[top]())
-        roofline.update({"bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "peak_source": hbm_src,
-                         "algorithmic_bytes_per_step": ab, "achieved": ab / (top_ms * 1e-3) / 1e9})
-        roofline["frac"] = roofline["achieved"] / hbm_peak
-    else:
-        # FP64-pipe bound kernels (north_star: "FP64-pipe utilisation against peak for the Riemann/flux kernel"):
-        # flops = FP64 operations of one launch of this kernel on this workload counted by ncu (DFMA = 2)
-        fl = (2.0 * kops["dfma"] + kops["dmul"] + kops["dadd"]) if kops else None
-        roofline.update({"bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
-                         "peak_source": "of measured (DFMA microbenchmark run live, mlh_measure_fp64_peak)",
-                         "flop_per_step": fl, "achieved": fl / (top_ms * 1e-3) / 1e12 if fl else None})
-        roofline["frac"] = roofline["achieved"] / fp64_peak if fl else None
-    # every kernel against BOTH rooflines (max(bytes/BW_peak, flops/FP64_peak) / t_measured): FP64 operations
-    # and DRAM bytes of one launch as ncu counted them for this workload (profiles/fp64_ops.json), algorithmic bytes where
-    # DESIGN.md section 3 has a model; "bound" = the roofline the kernel sits closer to
-    kernel_rooflines = {}
-    for k, ms_k in per_launch.items():
-        t = ms_k * 1e-3
-        e = {}
-        if k in ops:
-            o = ops[k]
-            e["fp64_frac"] = (2.0 * o["dfma"] + o["dmul"] + o["dadd"]) / t / 1e12 / fp64_peak
-            e["dram_frac"] = o.get("dram_bytes", 0.0) / t / 1e9 / hbm_peak
-        if k in hbm_models and nfaces is not None:
-            e["hbm_algorithmic_frac"] = float(hbm_models[k]()) / t / 1e9 / hbm_peak
-        if not e:
-            continue
-        hb = max(e.get("dram_frac", 0.0), e.get("hbm_algorithmic_frac", 0.0))
-        fb = e.get("fp64_frac", 0.0)
-        e["bound"] = "hbm" if hb >= fb else "fp64"
-        e["frac"] = max(hb, fb)
-        kernel_rooflines[k] = e
-    # HBM view of the whole step (algorithmic bytes)
-    hbm = {"unit": "GB/s", "peak": hbm_peak, "peak_source": hbm_src,
-           "step_achieved": ALL_ALGO_BYTES[D] * n_local / (step_ms_prof * 1e-3) / 1e9}
-    hbm["step_frac"] = hbm["step_achieved"] / hbm_peak
-    kernels = {k: {"ms_per_step": v[0] / psteps, "launches_per_step": v[1] / psteps} for k, v in prof.items() if v[1]}
+    if want_profile:
+        gpu.profile(True)
+        psteps = max(3, min(args.steps, 10))
+        for _ in range(psteps):
+            gpu.step(want_dt=False)
+        prof = gpu.profile_read()
+        gpu.profile(False)
+        res["prof"] = prof
+        res["psteps"] = psteps
+        res["noi_mean"] = float((gpu.fetch("noi").mean() + gpu.fetch("noiGhosts").mean()))  # rank 0's particles when sharded
+        res["nfaces"] = int(gpu.fetch("num_faces")[0])
 
     # ---- end to end through the C ABI with host buffers ----
-    e2e = None
-    if not args.no_e2e:
+    if want_e2e:
         # every rank: H2D of its shard from pinned host arrays, one step, D2H of the result.  Single GPU: the next step
         # starts from the downloaded state (host round trip).  Sharded: particles migrate between slabs, so the owned set
         # a rank downloads may differ from the one it uploaded; every step therefore uploads the rank's initial shard
@@ -372,27 +332,190 @@ def main():
         barrier()
         e_s = max_over_ranks(time.perf_counter() - t0)
         nb = len(names) * 8 * n_local
-        e2e = {"value": n_total * esteps / e_s, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb + 4 * n_local,
-               "steps": esteps, "ms_per_step": 1e3 * e_s / esteps,
-               "timing": "host wall clock (max over ranks) around upload+step+download, pinned buffers; bytes are rank 0's"}
+        res["e2e"] = {"value": n_total * esteps / e_s, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb + 4 * n_local,
+                      "steps": esteps, "ms_per_step": 1e3 * e_s / esteps,
+                      "timing": "host wall clock (max over ranks) around upload+step+download, pinned buffers; bytes are rank 0's"}
+    gpu.close()
+    return res
+
+
+def rooflines(res, local_rank):
+    """roofline object of the dominant kernel + every kernel against both rooflines (DESIGN.md sections 3 and 6)"""
+    from meshlesshydro_b200 import capi
+    D, n_local, nfaces, noi_mean = res["D"], res["n_local"], res["nfaces"], res["noi_mean"]
+    prof, psteps, wname = res["prof"], res["psteps"], res["wname"]
+    per_launch = {k: v[0] / psteps for k, v in prof.items() if v[1]}  # per STEP (a chunked kernel may launch more than once)
+    step_ms_prof = sum(v[0] for v in prof.values()) / psteps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "of measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "of fallback (B200_PROFILING.md 6.65 TB/s)"
+    fp64_peak = capi.fp64_peak_tflops(local_rank)
+    ops, ops_note = {}, None
+    try:
+        allops = json.load(open(os.path.join(ROOT, "profiles", "fp64_ops.json")))
+        ops = allops.get(wname, {})
+        if not ops and wname == "kh2000" and "kh1000" in allops:
+            # same flow, same neighbour count: per-launch counts scale with the particle count
+            ops = {k: {kk: vv * 4.0 for kk, vv in v.items()} for k, v in allops["kh1000"].items()}
+            ops_note = "ncu counts of kh1000 (1 M) x 4"
+    except Exception:
+        pass
+    top = max(per_launch.items(), key=lambda kv: prof[kv[0]][0])[0]
+    top_ms = per_launch[top]
+    nslots = n_local * noi_mean if noi_mean else None
+    frec = 4 if D == 2 else 6
+    # SURVEY 8(d) algorithmic bytes per launch (each per-particle array once per kernel that must touch it; lists and
+    # per-face staging excluded)
+    algo = {
+        "k1_gather": lambda: n_local * 2 * ((2 * D + 2) * 8 + 8),
+        "k4c_flux_sum_update": lambda: n_local * 2 * (2 * D + 2) * 8,
+    }
+    # bytes the kernel is DESIGNED to move (algorithmic + neighbour lists + per-face staging of the flux pass): what its
+    # measured DRAM traffic should be compared with -- not SURVEY's algorithmic figure
+    staged = {
+        "k4a_face_states": lambda: n_local * (2 * D + 4 + D * D + (D + 2) * D) * 8 + nfaces * ((4 * D + 4) * 8 + 8),
+        "k4c_flux_sum_update": lambda: nslots * (4 + frec * 8) + n_local * 2 * (2 * D + 2) * 8,
+        "k2b_face_index": lambda: nslots * 12 + nfaces * 8,
+        "k4b1_face_setup": lambda: nfaces * (6 * 8 + 11 * 8 + 4),
+        "k4b3_face_finish": lambda: nfaces * ((4 * D + 4) * 8 + 8 + frec * 8),
+    }
+    roofline = {"kernel": top, "share_of_step": prof[top][0] / psteps / step_ms_prof if step_ms_prof else None,
+                "ms_per_step": top_ms, "launches_per_step": prof[top][1] / psteps, "traffic": None,
+                "counts": "per step of this rank's shard" + ("; " + ops_note if ops_note else "")}
+    kops = ops.get(top)
+    scale_n = 1.0
+    if kops and res.get("world", 1) > 1:
+        scale_n = n_local / float(res["n_total"])  # ncu counted the single-GPU workload: this rank holds n_local of it
+    if kops:
+        roofline["traffic"] = kops.get("dram_bytes", 0.0) * scale_n
+    if top in algo and (nfaces is not None):
+        ab = float(algo[top]())
+        roofline.update({"bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "peak_source": hbm_src,
+                         "algorithmic_bytes_per_step": ab, "achieved": ab / (top_ms * 1e-3) / 1e9})
+        roofline["frac"] = roofline["achieved"] / hbm_peak
+    else:
+        # FP64-pipe bound kernels (north_star: "FP64-pipe utilisation against peak for the Riemann/flux kernel"):
+        # flops = FP64 operations of one launch of this kernel on this workload counted by ncu (DFMA = 2)
+        fl = (2.0 * kops["dfma"] + kops["dmul"] + kops["dadd"]) * scale_n if kops else None
+        roofline.update({"bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
+                         "peak_source": "of measured (DFMA microbenchmark run live, mlh_measure_fp64_peak)",
+                         "flop_per_step": fl, "achieved": fl / (top_ms * 1e-3) / 1e12 if fl else None})
+        roofline["frac"] = roofline["achieved"] / fp64_peak if fl else None
+    kernel_rooflines = {}
+    for k, ms_k in per_launch.items():
+        t = ms_k * 1e-3
+        e = {}
+        if k in ops:
+            o = ops[k]
+            e["fp64_frac"] = (2.0 * o["dfma"] + o["dmul"] + o["dadd"]) * scale_n / t / 1e12 / fp64_peak
+            e["dram_frac"] = o.get("dram_bytes", 0.0) * scale_n / t / 1e9 / hbm_peak
+        if k in algo and nfaces is not None:
+            e["hbm_algorithmic_frac"] = float(algo[k]()) / t / 1e9 / hbm_peak
+        if k in staged and nfaces is not None and nslots is not None:
+            e["staged_bytes_frac"] = float(staged[k]()) / t / 1e9 / hbm_peak
+        if not e:
+            continue
+        hb = max(e.get("dram_frac", 0.0), e.get("staged_bytes_frac", 0.0), e.get("hbm_algorithmic_frac", 0.0))
+        fb = e.get("fp64_frac", 0.0)
+        e["bound"] = "hbm" if hb >= fb else "fp64"
+        e["frac"] = max(hb, fb)
+        kernel_rooflines[k] = e
+    hbm = {"unit": "GB/s", "peak": hbm_peak, "peak_source": hbm_src,
+           "step_achieved": ALL_ALGO_BYTES[D] * n_local / (step_ms_prof * 1e-3) / 1e9}
+    hbm["step_frac"] = hbm["step_achieved"] / hbm_peak
+    kernels = {k: {"ms_per_step": v[0] / psteps, "launches_per_step": v[1] / psteps} for k, v in prof.items() if v[1]}
+    return roofline, kernel_rooflines, hbm, kernels
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="N=8: do not append the Sedov 256^3 run")
+    ap.add_argument("--no-check", action="store_true", help="N>1: skip the bitwise sharded-vs-single check")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    wl = workloads()
+    wname = args.workload or "kh2000"
+    factory, preset, wdesc = wl[wname]
+
+    # ---------------- reference arm ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        side = SIDES[wname]
+        if world > 1 and wname == "sedov61":
+            side = int(round(61 * world ** (1.0 / 3.0)))
+        res = time_reference(factory, preset, side, max(1, args.steps), max(0, min(args.warmup, 1)), budget_s=150.0)
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak" if wname == "sedov61" else "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wdesc, "n_particles_sample": res["n_particles"],
+                           "note": "the reference is serial and O(N) per step (plus its O(N N_ghost) ghost search): a per-particle "
+                                   "rate measured on a bounded sample of the same IC generator"},
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- B200 arm ----------------
+    # exactly ONE line may reach stdout; libraries (NCCL prints its version banner there) are sent to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the MFV path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    res = run_workload(args, wname, dist, rank, world, local_rank, want_profile=True, want_e2e=not args.no_e2e)
+    res["world"] = world
+    also = None
+    if world == 8 and args.workload is None and not args.no_also:
+        # BASELINE configs[4]: Sedov 3D 256^3 = 16.7 M particles, halo exchange across 8 x B200
+        a = run_workload(args, "sedov256", dist, rank, world, local_rank, want_profile=False, want_e2e=False)
+        also = {"sedov256": {"workload": a["wdesc"], "n_particles": a["n_total"], "value": a["value"], "unit": UNIT,
+                             "ms_per_step": a["ms_per_step"], "timed_region": a["timed_region"], "n_gpus": world,
+                             "device_flags": a["flags"]}}
+    check = None
+    if world > 1 and not args.no_check:
+        check = mgpu_bitwise_check(dist, local_rank, rank, world)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        side = {"sedov61": 61, "sedov128": 61, "sedov256": 61, "kh100": 100, "kh1000": 200, "kh2000": 200, "fb1000": 200}[wname]
-        cpu = time_reference(factory, preset, side, 2, 1, budget_s=25.0)
+        cpu = time_reference(factory, preset, CPU_SIDES[wname], 2, 1, budget_s=25.0)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        D, n_local = res["D"], res["n_local"]
+        roofline, kernel_rooflines, hbm, kernels = rooflines(res, local_rank)
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wdesc, "n_particles": n_total, "dim": D, "mean_neighbours": noi_mean,
-                           "kernel_size": ic["h"], "abs_mode": "INT_TRUNC (g++/libstdc++ build of the reference)",
+                "config": {"workload": res["wdesc"], "n_particles": res["n_total"], "dim": D, "mean_neighbours": res["noi_mean"],
+                           "kernel_size": res["h"], "abs_mode": "INT_TRUNC (g++/libstdc++ build of the reference)",
                            "l2": "no flush between steps; per-step working set %.0f MB vs 126 MB L2"
-                                 % (n_local * (ALL_ALGO_BYTES[D] + 4 * (noi_mean or 32) * 4) / 1e6),
+                                 % (n_local * (ALL_ALGO_BYTES[D] + 4 * (res["noi_mean"] or 32) * 4) / 1e6),
                            "parallelism": "slab%d" % world if world > 1 else "single"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "hbm_view": hbm,
-                "kernel_rooflines": kernel_rooflines, "num_faces": nfaces, "kernels": kernels, "cpu_baseline": cpu, "device_flags": flags}
+                "timed_region": res["timed_region"], "clocks": res["clocks"], "e2e": res.get("e2e"),
+                "gpu_launches": res["launches"] * args.steps, "gpu_launches_per_step": res["launches"],
+                "roofline": roofline, "hbm_view": hbm, "kernel_rooflines": kernel_rooflines, "num_faces": res["nfaces"],
+                "kernels": kernels, "cpu_baseline": cpu, "device_flags": res["flags"], "also": also, "mgpu_check": check}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    gpu.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
