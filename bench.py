@@ -270,7 +270,7 @@ def run_workload(args, wname, dist, rank, world, local_rank, want_profile=True, 
         gpu.step(want_dt=False)
     ms = gpu.timer_stop()
     barrier()
-    launches = (gpu.launch_count() - l0) / blocks
+    launches = gpu.launch_count() - l0  # kernels launched inside the timed region
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
     flags = gpu.error_flags()
@@ -512,7 +512,7 @@ def main():
                                  % (n_local * (ALL_ALGO_BYTES[D] + 4 * (res["noi_mean"] or 32) * 4) / 1e6),
                            "parallelism": "slab%d" % world if world > 1 else "single"},
                 "timed_region": res["timed_region"], "clocks": res["clocks"], "e2e": res.get("e2e"),
-                "gpu_launches": res["launches"] * args.steps, "gpu_launches_per_step": res["launches"],
+                "gpu_launches": res["launches"], "gpu_launches_per_step": res["launches"] / float(res["timed_region"]["steps_total"]),
                 "roofline": roofline, "hbm_view": hbm, "kernel_rooflines": kernel_rooflines, "num_faces": res["nfaces"],
                 "kernels": kernels, "cpu_baseline": cpu, "device_flags": res["flags"], "also": also, "mgpu_check": check}
         os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -216,7 +216,6 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k_neighbours_cell(const Params 
     __shared__ int s_id[K2_WARPS][32 * K2_MAXCH];             // candidate: original id
     __shared__ unsigned s_col[K2_WARPS][32 * K2_MAXCH];       // candidate: which particles of the batch list it (bit l)
     __shared__ unsigned s_m[K2_WARPS][K2_MAXP][K2_MAXCH + 1]; // hit mask of (particle, tile); +1: conflict-free columns
-    __shared__ unsigned short s_grp[K2_WARPS][NS][K2_MAXP + 2]; // group starts of the batch, written out row by row
     __shared__ int s_off[K2_WARPS][NS + 1];                   // first candidate number of each stencil cell
     __shared__ int s_start[K2_WARPS][NS];                     // first sorted index of each stencil cell
     if (threadIdx.x == 0) s_grid = *p.d.grid;
@@ -276,7 +275,8 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k_neighbours_cell(const Params 
                 idi = p.d.id[i_base + lane];
             }
             // lane l = particle l of the batch: its list so far
-            unsigned cnt = 0u, nown = 0u, gk = 0u; // entries, owned entries, next stencil cell whose group start is unwritten
+            unsigned cnt = 0u, nown = 0u; // entries, owned entries
+            int gk = 0;                   // next stencil cell whose group start is unwritten (warp-uniform)
             __syncwarp();
             for (int q0 = 0; q0 < total; q0 += 32 * K2_MAXCH) { // passes over the candidates (one in all but pathological cells)
                 const int npass = min(32 * K2_MAXCH, total - q0), ntile = (npass + 31) >> 5;
@@ -325,12 +325,13 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k_neighbours_cell(const Params 
                         for (int k = 0; k < D; ++k) xi[k] = s_x[w][k][l];
 #pragma unroll
                         for (int u = 0; u < K2_U; ++u) {
+                            if (c0 + u >= ntile) break; // (warp-uniform)
                             double d[3];
 #pragma unroll
                             for (int k = 0; k < D; ++k) d[k] = __dsub_rn(xj[u][k], xi[k]);
                             const bool hit = (dist_sqr_exact<D>(d) < p.hSqr) & (jj[u] != i); // Particles.cpp:341-347
                             const unsigned m = __ballot_sync(FULL, hit);
-                            if (lane == 0 && c0 + u < ntile) s_m[w][l][c0 + u] = m;
+                            if (lane == 0) s_m[w][l][c0 + u] = m;
                             col[u] |= hit ? (1u << l) : 0u;
                         }
                     }
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k_neighbours_cell(const Params 
                 __syncwarp();
                 // ---- emission: lane l walks the hit masks of particle l; every iteration emits the next hit of every
                 // particle, i.e. list slot `cnt` of consecutive particles -> one coalesced run per array ----
+                const unsigned cnt_before = cnt;
                 if (lane < nb) {
                     const unsigned i = (unsigned)(i_base + lane);
                     int t = 0;
@@ -351,28 +353,41 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k_neighbours_cell(const Params 
                         const int ql = t * 32 + (__ffs(m) - 1);
                         m &= m - 1u;
                         const unsigned enc = s_j[w][ql];
-                        const unsigned k = (unsigned)(NS - 1) - ((enc >> MLH_NNL_IDX_BITS) & 31u);
                         const unsigned slot = cnt++;
-                        // group starts: the stencil cells [gk, k] begin at this slot
-                        if (gk <= k) {
-                            const unsigned short gv = (unsigned short)(slot < max_ni ? slot : max_ni);
-                            do s_grp[w][gk][lane] = gv; while (++gk <= k);
-                        }
                         if (slot < max_ni) {
-                            const bool offr = (enc >> 31) != 0u;
                             const bool canon = idi < s_id[w][ql];
                             // owner = lower ORIGINAL index (Particles.cpp:1841,1889), or the only side with a list entry
+                            // (enc bit 31 = the partner is another rank's halo particle)
                             unsigned word = MLH_FMAP_SKIP; // the partner owns the pair and will fill this slot
-                            if (canon | offr) {
-                                word = MLH_K2_OWNED | (canon ? 0u : 1u) | (nown << MLH_K2_RANK_SHIFT) |
-                                       (b0 == 0 ? ((unsigned)__popc(s_col[w][ql] & ltl) << MLH_K2_R_SHIFT) : MLH_K2_R_OVER) |
-                                       (((enc >> MLH_NNL_IDX_BITS) & 31u) << MLH_K2_SC_SHIFT) | (offr ? MLH_K2_NOPARTNER : 0u);
+                            if (canon | ((int)enc < 0)) {
+                                // enc bits 26..31 (mirrored stencil cell, halo flag) are the word's bits 18..23
+                                static_assert(MLH_K2_SC_SHIFT == MLH_NNL_IDX_BITS - 8 && MLH_K2_NOPARTNER == (1u << 23), "field layout");
+                                word = (MLH_K2_OWNED | (nown << MLH_K2_RANK_SHIFT)) + (canon ? 0u : 1u) + ((enc >> 8) & 0xFC0000u) +
+                                       (b0 == 0 ? ((unsigned)__popc(s_col[w][ql] & ltl) << MLH_K2_R_SHIFT) : MLH_K2_R_OVER);
                                 ++nown;
                             }
                             const unsigned at = slot * ncap + i;
                             p.d.nnl[at] = (int)(enc & MLH_NNL_IDX_MASK);
                             p.d.fmap[at] = word;
                         }
+                    }
+                }
+                // ---- group starts (grp[k][i] = entries of i that lie in stencil cells before k): for every stencil cell whose
+                // first candidate falls into this pass, the hits of particle l before that candidate = (hits in the pass's
+                // earlier tiles) + popc(mask of its tile & lanes below it).  k and the tile are warp-uniform: no divergence,
+                // and a row of grp leaves as one run over the lanes ----
+                {
+                    unsigned pref = cnt_before; // entries of particle l before this pass
+                    int tcur = 0;
+                    while (gk < NS && s_off[w][gk] < q0 + npass) {
+                        const int ql = s_off[w][gk] - q0, ch = ql >> 5;
+                        for (; tcur < ch; ++tcur)
+                            if (lane < nb) pref += __popc(s_m[w][lane][tcur]);
+                        if (lane < nb) {
+                            const unsigned gv = pref + __popc(s_m[w][lane][ch] & ((1u << (ql & 31)) - 1u));
+                            p.d.grp[(unsigned)gk * ncap + (unsigned)(i_base + lane)] = (unsigned short)(gv < max_ni ? gv : max_ni);
+                        }
+                        ++gk;
                     }
                 }
                 __syncwarp(); // tables are rebuilt by the next pass
@@ -382,7 +397,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k_neighbours_cell(const Params 
                 const int i = i_base + lane;
                 if (cnt > max_ni) overflow = true;
                 const int nreg = (int)(cnt < max_ni ? cnt : max_ni);
-                for (; gk < (unsigned)NS; ++gk) s_grp[w][gk][lane] = (unsigned short)nreg;
+                for (int k = gk; k < NS; ++k) p.d.grp[(unsigned)k * ncap + (unsigned)i] = (unsigned short)nreg; // empty trailing cells
                 p.d.noi[i] = nreg;
                 int ng = 0;
                 if (PER) ng = ghost_entries<D>(p, g, i, c, nreg, &nown, &overflow);
@@ -391,9 +406,6 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k_neighbours_cell(const Params 
                 const unsigned len = (unsigned)(nreg + ng);
                 maxlen = len > maxlen ? len : maxlen;
             }
-            __syncwarp();
-            for (int k = 0; k < NS; ++k)
-                if (lane < nb) p.d.grp[(unsigned)k * ncap + (unsigned)(i_base + lane)] = s_grp[w][k][lane];
         }
     }
     if (overflow) atomicOr(p.d.flags, MLH_F_MAX_INTERACTIONS);

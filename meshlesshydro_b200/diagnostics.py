@@ -58,3 +58,90 @@ def conservation_drift(series):
     pscale = np.sqrt(2.0 * M * E)
     return {"mass": float(np.max(np.abs(a[:, 1] - M)) / M), "energy": float(np.max(np.abs(a[:, 2] - E)) / E),
             "momentum": float(np.max(np.abs(a[:, 3:6] - a[0, 3:6])) / pscale)}
+
+
+class SedovTaylor:
+    """Self-similar point-blast solution in a uniform medium (Sedov 1959; closed parametric form as in Book 1994,
+    "The Sedov self-similar point blast solutions in nonuniform media", with w = 0), the curve the reference's
+    PlotSedov.py draws over its snapshots (/root/reference/testcases/sedov/PlotSedov.py:17-175).
+
+    With V the similarity variable running from V_min = 2/((nu+2) gamma) (centre; shown here scaled by (nu+2)/2 as f)
+    to the shock, the profiles are products of powers of three linear factors of f.  R_s(t) = c (E t^2 / rho0)^(1/(nu+2))
+    where c follows from energy conservation: E = int (rho v^2/2 + P/(gamma-1)) dV.
+    """
+
+    def __init__(self, energy=1.0, rho0=1.0, gamma=5.0 / 3.0, nu=3, samples=200001):
+        g, n = float(gamma), int(nu)
+        if n not in (1, 2, 3):
+            raise ValueError("nu must be 1, 2 or 3")
+        self.E, self.rho0, self.gamma, self.nu = float(energy), float(rho0), g, n
+        # exponents of the three factors (uniform medium)
+        w1 = (3.0 * n - 2.0 + g * (2.0 - n)) / (g + 1.0)
+        w2 = (2.0 * (g - 1.0) + n) / g
+        w3 = n * (2.0 - g)
+        a0 = 1.0 / (n * g - n + 2.0)
+        a2 = (g - 1.0) / (g * w2)
+        a3 = n / (g * w2)
+        a5 = 2.0 * n / w3
+        a6 = 2.0 / (n + 2.0)
+        a1 = a2 + (g + 1.0) * a0 - a6
+        a4 = a1 * n * (n + 2.0) / w3
+        a8 = n * a6
+        k5 = 2.0 / (g - 1.0)
+        k6 = 0.5 * (g + 1.0)
+        k1 = k5 * g
+        k2 = k6 / g
+        k3 = (n * g - n + 2.0) / (w1 * k6)
+        k4 = (n + 2.0) * a0 * k6
+        f = np.logspace(np.log10(k2), 0.0, int(samples))[1:]  # from the centre (f -> k2) to the shock (f = 1)
+        A, B, C = k1 * (f - k2), k3 * (k4 - f), k5 * (k6 - f)
+        eta = f ** (-a6) * A ** a2 * B ** (-a1)          # r / R_s
+        dens = A ** a3 * B ** a4 * C ** (-a5)            # rho / rho_shock
+        pres = f ** a8 * B ** (a4 - 2.0 * a1) * C ** (1.0 - a5)  # P / P_shock
+        vel = eta * f                                    # v / v_shock
+        order = np.argsort(eta)
+        self._eta, self._d, self._p, self._v = eta[order], dens[order], pres[order], vel[order]
+        # normalisation: with the shock values rho_s = (g+1)/(g-1) rho0, v_s = 2/(g+1) D, P_s = 2/(g+1) rho0 D^2 and
+        # D = a6 R_s / t the energy integral gives  E t^2 / (rho0 R_s^(nu+2)) = alpha
+        geom = {1: 2.0, 2: 2.0 * np.pi, 3: 4.0 * np.pi}[n]
+        integrand = self._eta ** (n - 1) * (self._d * self._v ** 2 + self._p)
+        integral = np.sum(0.5 * (integrand[1:] + integrand[:-1]) * np.diff(self._eta))
+        alpha = integral * 8.0 * geom / ((g * g - 1.0) * (n + 2.0) ** 2)
+        self.xi0 = alpha ** (-1.0 / (n + 2.0))
+
+    def shock_radius(self, t):
+        return self.xi0 * (self.E * np.asarray(t, dtype=np.float64) ** 2 / self.rho0) ** (1.0 / (self.nu + 2.0))
+
+    def shock_speed(self, t):
+        return 2.0 / (self.nu + 2.0) * self.shock_radius(t) / t
+
+    @property
+    def post_shock_density(self):
+        return (self.gamma + 1.0) / (self.gamma - 1.0) * self.rho0
+
+    def density(self, r, t):
+        eta = np.asarray(r, dtype=np.float64) / self.shock_radius(t)
+        inside = np.interp(eta, self._eta, self._d, left=0.0) * self.post_shock_density
+        return np.where(eta <= 1.0, inside, self.rho0)
+
+    def pressure(self, r, t):
+        eta = np.asarray(r, dtype=np.float64) / self.shock_radius(t)
+        ps = 2.0 / (self.gamma + 1.0) * self.rho0 * self.shock_speed(t) ** 2
+        return np.where(eta <= 1.0, np.interp(eta, self._eta, self._p, left=self._p[0]) * ps, 0.0)
+
+    def velocity(self, r, t):
+        eta = np.asarray(r, dtype=np.float64) / self.shock_radius(t)
+        vs = 2.0 / (self.gamma + 1.0) * self.shock_speed(t)
+        return np.where(eta <= 1.0, np.interp(eta, self._eta, self._v, left=0.0) * vs, 0.0)
+
+
+def sedov_front(x, y, z, rho, rho0=1.0, nbins=40, rmax=0.5):
+    """(radius of the densest shell, its mean density, radius where the shell density last exceeds the mean of
+    background and peak -- the half-rise point of the front seen from outside)"""
+    rc, mean, cnt = radial_profile(x, y, z, rho, nbins, rmax)
+    ok = cnt > 0
+    rc, mean = rc[ok], mean[ok]
+    kmax = int(np.nanargmax(mean))
+    half = 0.5 * (mean[kmax] + rho0)
+    above = np.nonzero(mean >= half)[0]
+    return float(rc[kmax]), float(mean[kmax]), float(rc[above[-1]])
