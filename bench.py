@@ -247,7 +247,15 @@ def run_workload(args, wname, dist, rank, world, local_rank, want_profile=True, 
         return float(t.item())
 
     # ---- device-resident throughput ----
-    for _ in range(max(args.warmup - 2, 1)):
+    # The timed region is `blocks` blocks of --steps steps.  Every block starts from the initial condition (re-uploaded,
+    # plus one step, both untimed): the reference's scheme is not stable on the Sedov blast -- its CPU restatement turns
+    # NaN near t = 0.015 (tests/test_gpu_fullrun.py) -- so a benchmark that simply kept stepping for 0.6 s would leave the
+    # regime in which the step does meaningful work.  ms = sum of the blocks' CUDA-event times (max over ranks per block).
+    def restart():
+        gpu.upload(ic_local, ids=ids_local)
+        gpu.step(want_dt=False)
+
+    for _ in range(max(args.warmup - 3, 0)):
         gpu.step(want_dt=False)
     barrier()
     gpu.timer_start()
@@ -263,25 +271,31 @@ def run_workload(args, wname, dist, rank, world, local_rank, want_profile=True, 
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    l0 = gpu.launch_count()
-    barrier()
-    gpu.timer_start()
-    for _ in range(args.steps * blocks):
-        gpu.step(want_dt=False)
-    ms = gpu.timer_stop()
-    barrier()
-    launches = gpu.launch_count() - l0  # kernels launched inside the timed region
+    ms, launches = 0.0, 0
+    for _ in range(blocks):
+        restart()
+        l0 = gpu.launch_count()
+        barrier()
+        gpu.timer_start()
+        for _ in range(args.steps):
+            gpu.step(want_dt=False)
+        ms_b = gpu.timer_stop()
+        barrier()
+        launches += gpu.launch_count() - l0  # kernels launched inside the timed blocks
+        ms += max_over_ranks(ms_b)
     clocks = sampler.stop() if rank == 0 else None
-    ms = max_over_ranks(ms)
     flags = gpu.error_flags()
     nsteps = args.steps * blocks
     value = n_total * nsteps / (ms * 1e-3)
     res = {"wname": wname, "wdesc": wdesc, "scaling": scaling, "D": D, "n_total": n_total, "n_local": n_local, "value": value,
-           "ms_per_step": ms / nsteps, "timed_region": {"blocks": blocks, "steps_total": nsteps, "seconds": ms * 1e-3},
+           "ms_per_step": ms / nsteps,
+           "timed_region": {"blocks": blocks, "steps_total": nsteps, "seconds": ms * 1e-3,
+                            "note": "every block of --steps steps starts from the re-uploaded initial condition (+1 step), untimed"},
            "launches": launches, "clocks": clocks, "flags": flags, "h": ic["h"]}
 
     # ---- per-kernel profile (separate, untimed pass) for the roofline object ----
     if want_profile:
+        restart()
         gpu.profile(True)
         psteps = max(3, min(args.steps, 10))
         for _ in range(psteps):
@@ -474,6 +488,17 @@ def main():
         return 0
 
     # ---------------- B200 arm ----------------
+    # a rank that fails must not leave the others waiting in an NCCL call until the launcher's timeout: leave at once
+    # (torchrun then stops the peers); and no run may sit for more than 25 minutes whatever happens
+    import signal
+    import traceback
+
+    def _bail(*_):
+        sys.stderr.write("bench.py: watchdog / failure on rank %d\n" % rank)
+        traceback.print_stack()
+        os._exit(3)
+    signal.signal(signal.SIGALRM, _bail)
+    signal.alarm(1500)
     # exactly ONE line may reach stdout; libraries (NCCL prints its version banner there) are sent to stderr
     json_fd = os.dup(1)
     os.dup2(2, 1)
@@ -484,7 +509,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    res = run_workload(args, wname, dist, rank, world, local_rank, want_profile=True, want_e2e=not args.no_e2e)
+    try:
+        res = run_workload(args, wname, dist, rank, world, local_rank, want_profile=True, want_e2e=not args.no_e2e)
+    except Exception:
+        traceback.print_exc()
+        os._exit(2)
     res["world"] = world
     also = None
     if world == 8 and args.workload is None and not args.no_also:

@@ -1145,8 +1145,14 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_fac
 #endif
 
 
+#ifndef MLH_SETUP_BLOCKS
+#define MLH_SETUP_BLOCKS 8
+#endif
+#ifndef MLH_SETUP_PREFETCH
+#define MLH_SETUP_PREFETCH 1
+#endif
 template <int D>
-__global__ void __launch_bounds__(MLH_FACE_TILE, 8) k_face_setup(const Params p, const double *__restrict__ stage, double *__restrict__ pstar,
+__global__ void __launch_bounds__(MLH_FACE_TILE, MLH_SETUP_BLOCKS) k_face_setup(const Params p, const double *__restrict__ stage, double *__restrict__ pstar,
                                                               double *__restrict__ qd, int *__restrict__ qi, int *__restrict__ qcount,
                                                               int f0, int cstride) {
     const int nfaces = min(p.d.face_start[p.own_end], p.fcap);
@@ -1155,16 +1161,44 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, 8) k_face_setup(const Params p,
     const int nround = (f1 - f0 + 31) / 32 * 32; // whole warps stay in the loop (ballots in face_setup_and_queue)
     const int rcap = q_region_cap(cstride);
     using R = FaceRec<D>;
-    for (int fl = blockIdx.x * MLH_FACE_TILE + threadIdx.x; fl < nround; fl += gridDim.x * MLH_FACE_TILE) {
+    // the six fields of the NEXT trip are requested before this trip's ~600 instructions run (the kernel waited on its
+    // loads at 46 % occupancy: long_scoreboard 8.5 of 15 stalled warps, profiles/r02_k_face_setup_ncu_full.txt)
+    const int stride = gridDim.x * MLH_FACE_TILE;
+    int fl = blockIdx.x * MLH_FACE_TILE + threadIdx.x;
+    double wn[6] = {1., 1., 0., 1., 1., 0.};
+    bool vn = fl < nround && f0 + fl < f1;
+    if (vn) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) wn[k] = stage[k * fs + fl];
+    }
+#if !MLH_SETUP_PREFETCH
+    for (; fl < nround; fl += stride) { // (A/B variant: fields loaded when the trip starts)
         const bool valid = f0 + fl < f1;
         double w[6] = {1., 1., 0., 1., 1., 0.};
         if (valid) {
-            const double *rec = stage + fl;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) w[k] = rec[k * fs];
+            for (int k = 0; k < 6; ++k) w[k] = stage[k * fs + fl];
         }
         face_setup_and_queue(p, valid, fl, w[R::RHOL], w[R::PL], w[R::UL], w[R::RHOR], w[R::PR], w[R::UR], pstar, qd, qi, qcount, rcap);
     }
+    (void)vn;
+    (void)wn;
+    (void)stride;
+#else
+    for (; fl < nround; fl += stride) {
+        const bool valid = vn;
+        double w[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[k] = wn[k];
+        const int fnext = fl + stride;
+        vn = fnext < nround && f0 + fnext < f1;
+        if (vn) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) wn[k] = stage[k * fs + fnext];
+        }
+        face_setup_and_queue(p, valid, fl, w[R::RHOL], w[R::PL], w[R::UL], w[R::RHOR], w[R::PR], w[R::UR], pstar, qd, qi, qcount, rcap);
+    }
+#endif
 }
 
 // One queued face per lane, iteration state in registers, no block-level synchronisation.  Each warp owns a ring of
