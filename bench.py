@@ -255,24 +255,15 @@ def run_workload(args, wname, dist, rank, world, local_rank, want_profile=True, 
         gpu.upload(ic_local, ids=ids_local)
         gpu.step(want_dt=False)
 
-    for _ in range(max(args.warmup - 3, 0)):
+    for _ in range(args.warmup):
         gpu.step(want_dt=False)
     barrier()
-    gpu.timer_start()
-    for _ in range(2):  # the last two warm-up steps also size the timed region
-        gpu.step(want_dt=False)
-    est_ms = max_over_ranks(gpu.timer_stop()) / 2.0
-    blocks = max(1, int(np.ceil(600.0 / max(est_ms * args.steps, 1e-3))))  # >= 0.6 s of steps in the region
-    if world > 1:
-        t = torch.tensor([blocks], dtype=torch.int64, device="cuda")
-        dist.broadcast(t, src=0)
-        blocks = int(t.item())
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    ms, launches = 0.0, 0
-    for _ in range(blocks):
+    ms, launches, blocks = 0.0, 0, 0
+    while ms < 600.0 and blocks < 400:  # >= 0.6 s of timed steps (ms is the max over ranks: the same on every rank)
         restart()
         l0 = gpu.launch_count()
         barrier()
@@ -283,6 +274,7 @@ def run_workload(args, wname, dist, rank, world, local_rank, want_profile=True, 
         barrier()
         launches += gpu.launch_count() - l0  # kernels launched inside the timed blocks
         ms += max_over_ranks(ms_b)
+        blocks += 1
     clocks = sampler.stop() if rank == 0 else None
     flags = gpu.error_flags()
     nsteps = args.steps * blocks

@@ -1149,7 +1149,9 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_fac
 #define MLH_SETUP_BLOCKS 8
 #endif
 #ifndef MLH_SETUP_PREFETCH
-#define MLH_SETUP_PREFETCH 1
+// requesting the next trip's six fields before this trip computes LOST (A/B r2g, Sedov 61^3 / KH 1M: 0.131 -> 0.143 ms,
+// 1.259 -> 1.339 ms at 8 blocks/SM with spills; 0.129 / 1.327 at 6 blocks without): off
+#define MLH_SETUP_PREFETCH 0
 #endif
 template <int D>
 __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_SETUP_BLOCKS) k_face_setup(const Params p, const double *__restrict__ stage, double *__restrict__ pstar,
@@ -1161,8 +1163,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_SETUP_BLOCKS) k_face_setup(
     const int nround = (f1 - f0 + 31) / 32 * 32; // whole warps stay in the loop (ballots in face_setup_and_queue)
     const int rcap = q_region_cap(cstride);
     using R = FaceRec<D>;
-    // the six fields of the NEXT trip are requested before this trip's ~600 instructions run (the kernel waited on its
-    // loads at 46 % occupancy: long_scoreboard 8.5 of 15 stalled warps, profiles/r02_k_face_setup_ncu_full.txt)
+    // (MLH_SETUP_PREFETCH: the six fields of the NEXT trip requested before this trip's ~600 instructions run)
     const int stride = gridDim.x * MLH_FACE_TILE;
     int fl = blockIdx.x * MLH_FACE_TILE + threadIdx.x;
     double wn[6] = {1., 1., 0., 1., 1., 0.};

@@ -89,3 +89,98 @@ def test_sedov_run_diagnostics():
     E = so[0][2]
     print("Sedov 16^3, 40 steps: t=%.5e E=%.4f analytic R_s=%.3f, worst state error %.1e"
           % (t_o, E, DG.sedov_shock_radius_analytic(E, 1.0, t_o), worst))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The shipped cases at their shipped length, against what the reference's own scripts plot
+# ---------------------------------------------------------------------------------------------------------------------
+def test_sedov_shipped_case_against_similarity_solution():
+    """testcases/sedov: N = 31^3, kernelSize 0.07, CFL 0.25, pairwise limiter (config.info, parameter.h); the reference's
+    PlotSedov.py:17-211 draws rho(r) over the Sedov-Taylor similarity solution -- here as numbers (diagnostics.SedovTaylor
+    restates that curve, diagnostics.sedov_front reads the front off 40 radial shells).
+
+    Length of the run: the shipped timeEnd = 10 cannot be reached by the reference's algorithm itself -- its CPU
+    restatement (oracle, pinned to the reference sources) turns NaN on this blast at t ~ 0.015-0.03 (step ~28 at 31^3, in
+    both `abs` modes; the reference README says of this case "throws some errors as it is not fully debugged yet").  The
+    comparison is therefore made at t = 0.010, while the blast (R_s = 0.18) is still inside the well-behaved regime, with
+    the quirk switches set to the evident intent (fabs, geometric |x_j - x_i|).
+
+    Stated tolerances (kernel support 0.07 = 2.2 particle spacings smears the front over ~0.1):
+      * radius of the densest shell within 0.02 (0.6 spacings) of R_s(t) = xi0 (E t^2 / rho0)^(1/5),
+        half-rise point of the front outside R_s - 0.01;
+      * peak shell density between 1.3 and the strong-shock limit 4 rho0; at 61^3 (kernel half as wide) it is higher;
+      * mass and energy conserved to 1e-12 over the run."""
+    t_end = 0.010
+    fronts = {}
+    for n in (31, 61):
+        ic = IC.sedov(n)
+        if n == 31:
+            ic["h"] = 0.07  # testcases/sedov/config.info:33
+        cfg = capi.make_config("sedov3d", ic["h"], ic["gamma"], None, abs_mode=capi.ABS_FABS, q13_mode=capi.Q13_GEOMETRIC,
+                               max_interactions=200)
+        gpu = capi.MfvGpu(cfg)
+        gpu.upload(ic)
+        s0 = gpu.sums()
+        t, steps = 0.0, 0
+        while t < t_end * (1.0 - 1e-12):
+            t += gpu.step(dt_max=t_end - t)
+            steps += 1
+            assert steps < 2000
+        gpu.prepare()  # rho of the final state
+        s1 = gpu.sums()
+        assert gpu.error_flags() == 0
+        assert abs(s1[1] - s0[1]) <= 1e-12 * s0[1] and abs(s1[2] - s0[2]) <= 1e-12 * s0[2], (s0, s1)
+        st = gpu.download_state()
+        rho = gpu.fetch("rho")
+        assert not np.isnan(rho).any()
+        sol = DG.SedovTaylor(energy=s0[2], rho0=1.0, gamma=ic["gamma"], nu=3)
+        r_ana = float(sol.shock_radius(t))
+        r_peak, rho_peak, r_half = DG.sedov_front(st["x"], st["y"], st["z"], rho, rho0=1.0, nbins=40, rmax=0.5)
+        fronts[n] = (r_ana, r_peak, rho_peak, r_half, steps)
+        print("Sedov %d^3 t=%.4f (%d steps): R_s analytic %.4f, densest shell %.4f (rho %.3f), half-rise %.4f"
+              % (n, t, steps, r_ana, r_peak, rho_peak, r_half))
+        assert abs(r_peak - r_ana) <= 0.02, fronts[n]
+        assert r_half >= r_ana - 0.01, fronts[n]
+        assert 1.3 <= rho_peak <= 4.0, fronts[n]
+        gpu.close()
+    assert abs(fronts[31][0] - 0.1822) <= 2e-3  # xi0 = 1.152 for gamma = 5/3
+    assert fronts[61][2] > fronts[31][2], "the front must sharpen with resolution"
+
+
+def test_kelvin_helmholtz_shipped_long_run():
+    """testcases/kelvin-helmholtz: N = 10^4, kernelSize 0.04, CFL 0.4, timeEnd 15 (config_long_run.info,
+    parameter_long_run.h); conservationPlotter.py plots the per-snapshot sums against time.  ~5000 adaptive steps
+    through the C ABI, sums sampled every 0.025 time units (h5DumpInterval 5 x timeStep 0.005).
+
+    Initial condition: the generator's lattice, jittered by 0.2 spacings (tie-free periodic seam, quirk Q9; random
+    positions make the reference's own arithmetic produce NaN in the first step at this N).
+    Stated tolerances: mass 1e-12, energy and momentum 1e-11 relative drift over the WHOLE run (round-off only: every
+    face adds +F and -F); no device flags, no NaN; the seeded vy mode has grown 5-9x by t = 2.5 (CPU oracle: 6.64x)."""
+    ic = IC.kelvin_helmholtz(100, lattice=True, jitter=0.2)
+    cfg = capi.make_config("kh2d", ic["h"], ic["gamma"], ic.get("box"), abs_mode=capi.ABS_FABS, max_interactions=160)
+    gpu = capi.MfvGpu(cfg)
+    gpu.upload(ic)
+    a0 = DG.kh_mode_amplitude(ic["x"], ic["vy"], ic["m"])
+    t_end, dump = 15.0, 0.025
+    series, t, steps, nxt, a25 = [gpu.sums()], 0.0, 0, dump, None
+    while t < t_end * (1.0 - 1e-12):
+        t += gpu.step(dt_max=nxt - t)
+        steps += 1
+        assert steps < 20000
+        if t >= nxt * (1.0 - 1e-12):
+            series.append(gpu.sums())
+            nxt += dump
+            if a25 is None and t >= 2.5:
+                st = gpu.download_state()
+                a25 = DG.kh_mode_amplitude(st["x"], st["vy"], st["m"])
+    flags = gpu.error_flags()
+    assert flags & ~capi.F_NEG_GHOST_PRESSURE == 0, flags
+    drift = DG.conservation_drift(series)
+    st = gpu.download_state()
+    assert not any(np.isnan(st[k]).any() for k in ("x", "y", "vx", "vy", "m", "u"))
+    a_end = DG.kh_mode_amplitude(st["x"], st["vy"], st["m"])
+    print("KH 100^2 to t=%.1f: %d steps, %d snapshots, drift %s, mode amplitude x%.2f at t=2.5, x%.2f at the end, one-sided seam pairs %d"
+          % (t, steps, len(series), {k: "%.1e" % v for k, v in drift.items()}, a25 / a0, a_end / a0, int(gpu.fetch("counters")[0])))
+    assert drift["mass"] <= 1e-12 and drift["energy"] <= 1e-11 and drift["momentum"] <= 1e-11, drift
+    assert 5.0 <= a25 / a0 <= 9.0, a25 / a0
+    gpu.close()
