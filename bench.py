@@ -263,7 +263,7 @@ def run_workload(args, wname, dist, rank, world, local_rank, want_profile=True, 
         sampler.start()
         time.sleep(0.25)
     ms, launches, blocks = 0.0, 0, 0
-    while ms < 600.0 and blocks < 400:  # >= 0.6 s of timed steps (ms is the max over ranks: the same on every rank)
+    while (ms < 1e3 * args.min_seconds or blocks < 1) and blocks < 400:  # >= 0.6 s of timed steps (ms = max over ranks: same on every rank)
         restart()
         l0 = gpu.launch_count()
         barrier()
@@ -447,6 +447,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="N=8: do not append the Sedov 256^3 run")
+    ap.add_argument("--min-seconds", type=float, default=0.6, help="length of the timed region (0: one block of --steps; profiler runs)")
     ap.add_argument("--no-check", action="store_true", help="N>1: skip the bitwise sharded-vs-single check")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -81,7 +81,7 @@ typedef struct {
     int rank, nranks;         /* slab decomposition over GPUs of one node (nranks<=1: single GPU) */
     long capacity;            /* particle capacity of this rank incl. halo; 0 -> derived from N */
     long stage_bytes;         /* budget of the per-face staging buffer of the flux pass (it replaces the reference's
-                                 per-slot WijL/WijR/Aij/Fij arrays, Particles.h:201-229); 0 -> 6 GiB.  Particles are
+                                 per-slot WijL/WijR/Aij/Fij arrays, Particles.h:201-229); 0 -> 1/8 of the device memory.  Faces are
                                  processed in chunks that fit the budget. */
 } mlh_config;
 
