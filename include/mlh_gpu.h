@@ -173,6 +173,9 @@ int mlh_grid_info(mlh_ctx *ctx, int *cells3, double *cell_size3, double *bounds6
  *          its partner b, and the image code of b in a's list; "face_rec" -> double[F*(4*DIM+4)]: the reference's
  *          per-slot WijR[a-slot] (state of a), WijL (state of b), vFrame, Aij (Particles.cpp:1290-1311,1488-1733);
  *          "face_F" -> double[F*(DIM+2)]: Fij of that slot (Particles.cpp:1787-1911).
+ * "flux_symmetry" -> int[4] = Particles::checkFluxSymmetry (Particles.cpp:2888-2976) in structural form: slots with a
+ *          face, violations (must be 0), faces used from both sides, faces only their owner uses (partner on another
+ *          rank / one-sided seam pair, quirk Q9).  Valid after mlh_neighbours.
  * Returns the element count written, or <0.  dst NULL -> just the count.
  */
 long mlh_debug_fetch(mlh_ctx *ctx, const char *field, void *dst, long dst_elems);

@@ -104,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "mlh_slab_range", "mlh_host_alloc", "mlh_host_free", "mlh_measure_fp64_peak", "mlh_riemann_faces",
 ]
 
-_INT_FIELDS = {"cell", "noi", "noiGhosts", "sorted_index", "nnl", "nnlGhosts", "nnlGhostCodes", "num_faces", "face_pairs"}
+_INT_FIELDS = {"cell", "noi", "noiGhosts", "sorted_index", "nnl", "nnlGhosts", "nnlGhostCodes", "num_faces", "face_pairs", "flux_symmetry"}
 
 
 def _dp(a):

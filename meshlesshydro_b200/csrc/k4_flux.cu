@@ -1653,8 +1653,20 @@ int riemann_faces(mlh_ctx *c, int n, const double *hWL, const double *hWR, const
     const size_t nd_in = (size_t)n * (2 * NW + 2 * D);
     const size_t doubles = nd_in + (size_t)FaceRec<D>::NREC * chunk + chunk + MLH_Q_FIELDS * qs + (size_t)n * MLH_FREC(D) + (size_t)n * NW;
     const size_t bytes = doubles * sizeof(double) + (qs + 2 * MLH_Q_REGIONS + 8) * sizeof(int);
-    char *buf = nullptr;
-    MLH_CUDA_CHECK(c, cudaMalloc(&buf, bytes));
+    // the host mirror of the reference's Riemann class calls this once per face (Riemann.h:19,26): the device scratch is
+    // kept between calls and only grows
+    if (bytes + 16 > c->rf_bytes) {
+        if (c->rf_buf) {
+            cudaStreamSynchronize(st);
+            cudaFree(c->rf_buf);
+            c->rf_buf = nullptr;
+            c->rf_bytes = 0;
+        }
+        const size_t want = bytes + 16 < ((size_t)1 << 20) ? ((size_t)1 << 20) : bytes + 16;
+        MLH_CUDA_CHECK(c, cudaMalloc(&c->rf_buf, want));
+        c->rf_bytes = want;
+    }
+    char *buf = c->rf_buf;
     double *dWL = (double *)buf, *dWR = dWL + (size_t)n * NW, *dvF = dWR + (size_t)n * NW, *dA = dvF + (size_t)n * D;
     double *stage = dA + (size_t)n * D;
     double *pstar = stage + (size_t)FaceRec<D>::NREC * chunk;
@@ -1676,9 +1688,8 @@ int riemann_faces(mlh_ctx *c, int n, const double *hWL, const double *hWR, const
     p.d.face_start = nfaces;
     p.fcap = n;
     p.d.F = F;
-    unsigned *flags = nullptr;
-    if (!p.d.flags) { // context without particles: private flag word
-        cudaMalloc(&flags, sizeof(unsigned));
+    if (!p.d.flags) { // context without particles: private flag word at the end of the scratch
+        unsigned *flags = (unsigned *)(buf + ((bytes + 7) / 8 * 8));
         cudaMemsetAsync(flags, 0, sizeof(unsigned), st);
         p.d.flags = flags;
     }
@@ -1691,8 +1702,6 @@ int riemann_faces(mlh_ctx *c, int n, const double *hWL, const double *hWR, const
     c->launches += 5;
     cudaMemcpyAsync(hF, out, sizeof(double) * n * NW, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(buf);
-    if (flags) cudaFree(flags);
     if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "mlh_riemann_faces: %s", cudaGetErrorString(e));
         return MLH_E_CUDA;

@@ -409,6 +409,7 @@ int mlh_destroy(mlh_ctx *c) {
     mlh_comm_destroy(c);
     if (c->pool) cudaFree(c->pool);
     if (c->dl_scratch) cudaFree(c->dl_scratch);
+    if (c->rf_buf) cudaFree(c->rf_buf);
     if (c->stage) cudaFree(c->stage);
     if (c->p.d.cell_count) {
         cudaFree(c->p.d.cell_count);
@@ -817,8 +818,10 @@ int mlh_download_diag(mlh_ctx *c, double *rho, double *P, double *rhoGrad, int *
     }
     const int o = p.own_begin, n = p.own_end - p.own_begin, D = p.D;
     const int *ids = p.d.id + o;
-    double *tmp = nullptr;
-    MLH_CUDA_CHECK(c, cudaMalloc(&tmp, sizeof(double) * (size_t)n * D));
+    // un-permutation scratch shared with mlh_download_state (8 x ncap doubles, allocated once): dump2file calls this
+    // at every snapshot (MeshlessScheme.cpp:165-195)
+    if (!c->dl_scratch) MLH_CUDA_CHECK(c, cudaMalloc(&c->dl_scratch, sizeof(double) * (size_t)c->p.ncap * 8));
+    double *tmp = c->dl_scratch;
     int rc = MLH_OK;
     auto one = [&](const double *src, double *dst) {
         if (!dst || rc != MLH_OK) return;
@@ -856,7 +859,6 @@ int mlh_download_diag(mlh_ctx *c, double *rho, double *P, double *rhoGrad, int *
         }
         cudaStreamSynchronize(c->stream);
     }
-    cudaFree(tmp);
     return rc;
 }
 
@@ -973,6 +975,40 @@ __global__ void k_export_face_flux(const Params p, int nfaces, double *out) {
     if (f >= nfaces) return;
     for (int nu = 0; nu < p.D + 2; ++nu) out[(size_t)f * (p.D + 2) + nu] = p.d.F[(size_t)f * MLH_FREC(p.D) + nu];
 }
+// Particles::checkFluxSymmetry (Particles.cpp:2888-2976) for the unique-face layout: the reference compares Fij + Fji of
+// every slot pair against FLUX_SYM_TOL; here both endpoints read ONE stored flux, so the check is structural -- every
+// slot must map to a face whose record names this particle (as owner or as the owner's list entry) and the two
+// endpoints must add it with opposite signs.  out[0] slots with a face, [1] violations, [2] faces used from both
+// sides, [3] faces only their owner uses (partner on another rank, or one-sided seam pair, quirk Q9: where the
+// reference prints "fluxes are NOT symmetric").
+__global__ void k_check_flux_symmetry(const Params p, unsigned long long *out) {
+    const int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned slots = 0, bad = 0, partner = 0, owned = 0;
+    if (i < p.own_end) {
+        const int ntot = p.d.noi[i] + p.d.noig[i];
+        for (int s = 0; s < ntot; ++s) {
+            const size_t at = (size_t)s * p.ncap + i;
+            const unsigned v = p.d.fmap[at];
+            if (v == MLH_FMAP_SKIP) continue;
+            const int f = (int)(v >> 2);
+            if (f >= p.fcap) continue;
+            ++slots;
+            const int fav = p.d.fa[f], e = p.d.fe[f];
+            const int owner = fav & 0x7FFFFFFF, j = p.d.nnl[at] & MLH_NNL_IDX_MASK;
+            if (v & 2u) { // this particle owns the face
+                ++owned;
+                if (owner != i || (e & MLH_NNL_IDX_MASK) != j || ((unsigned)fav >> 31) != (v & 1u)) ++bad;
+            } else {      // the partner owns it: it must name this particle, and add +F where this one adds -F
+                ++partner;
+                if (owner != j || (e & MLH_NNL_IDX_MASK) != i || !(v & 1u) || ((unsigned)fav >> 31) != 0u) ++bad;
+            }
+        }
+    }
+    atomicAdd(out + 0, (unsigned long long)slots);
+    atomicAdd(out + 1, (unsigned long long)bad);
+    atomicAdd(out + 2, (unsigned long long)partner);
+    atomicAdd(out + 3, (unsigned long long)(owned));
+}
 __global__ void k_iota_sorted_index(const Params p, int *out) {
     int i = p.own_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.own_end) return;
@@ -996,7 +1032,7 @@ extern "C" long mlh_debug_fetch(mlh_ctx *c, const char *field, void *dst, long d
             cudaStreamSynchronize(c->stream);
             return n;
         }
-        if (f != "num_faces" && f != "counters" && f != "one_sided_pairs") {
+        if (f != "num_faces" && f != "counters" && f != "one_sided_pairs" && f != "flux_symmetry") {
             snprintf(c->err, sizeof(c->err), "mlh_debug_fetch(%s) is single-GPU only", field);
             return MLH_E_INVALID;
         }
@@ -1136,6 +1172,24 @@ extern "C" long mlh_debug_fetch(mlh_ctx *c, const char *field, void *dst, long d
         cudaStreamSynchronize(c->stream);
         cudaFree(tmp);
         return count;
+    }
+    if (f == "flux_symmetry") { // Particles::checkFluxSymmetry, structural form (see k_check_flux_symmetry)
+        if (!dst) return 4;
+        if (dst_elems < 4) return MLH_E_INVALID;
+        unsigned long long *tmp = nullptr;
+        if (cudaMalloc(&tmp, 4 * sizeof(unsigned long long)) != cudaSuccess) return MLH_E_CUDA;
+        cudaMemsetAsync(tmp, 0, 4 * sizeof(unsigned long long), c->stream);
+        k_check_flux_symmetry<<<mlh_blocks(n > 0 ? n : 1, 128), 128, 0, c->stream>>>(p, tmp);
+        unsigned long long h[4];
+        cudaMemcpyAsync(h, tmp, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(tmp);
+        int *o4 = (int *)dst;
+        o4[0] = (int)std::min<unsigned long long>(h[0], 2147483647ull);
+        o4[1] = (int)std::min<unsigned long long>(h[1], 2147483647ull);
+        o4[2] = (int)std::min<unsigned long long>(h[2], 2147483647ull);
+        o4[3] = (int)std::min<unsigned long long>(h[3] - h[2], 2147483647ull); // owned faces without a partner slot
+        return 4;
     }
     if (f == "num_faces") { // faces of this step's list (k_face_index)
         if (!dst) return 1;

@@ -320,7 +320,9 @@ struct mlh_ctx {
     double *stage;       // face staging buffer of K4 (k4_flux.cu): record, P*, solver queue x stage_chunk
     int stage_chunk;     // faces per K4 chunk (multiple of 128)
     int num_sms;
-    double *dl_scratch;  // un-permutation staging of mlh_download_state (8 x ncap doubles, lazily allocated)
+    double *dl_scratch;  // un-permutation staging of mlh_download_state / mlh_download_diag (8 x ncap doubles, lazily allocated)
+    char *rf_buf;        // device scratch of mlh_riemann_faces (the reference's per-face Riemann class: kept between calls)
+    size_t rf_bytes;
     int max_cells;       // allocated cell-array size
     // pinned host mirror for small readbacks
     double *h_small;     // pinned

@@ -345,7 +345,23 @@ void Particles::compRiemannStatesLR(const double &, const double &, const double
 void Particles::compRiemannStatesLR(const double &, const double &, const double &, const Particles &) { ensure(PH_GRADIENTS); }
 void Particles::solveRiemannProblems(const double &, const Particles &) { ensure(PH_GRADIENTS); }
 void Particles::collectFluxes(Helper &, const Particles &) { ensure(PH_GRADIENTS); }
-void Particles::checkFluxSymmetry(Particles *) {} // each face is solved once; +-F is exact by construction
+// Particles::checkFluxSymmetry (reference Particles.cpp:2888-2976, called when DEBUG_LVL > 1): every pair of the lists is
+// ONE stored flux that both endpoints add with opposite signs, so Fij + Fji == 0 exactly; what can still go wrong is the
+// slot -> face map, which the device verifies (mlh_debug_fetch "flux_symmetry").  One-sided periodic pairs (quirk Q9) are
+// where the reference prints "fluxes are NOT symmetric".
+void Particles::checkFluxSymmetry(Particles *) {
+    if (ghostHolder || !gpu || phase < PH_NEIGHBOURS) return;
+    // the reference pays 11 % of its step for this check whenever DEBUG_LVL is set; here it costs a kernel and a
+    // read-back, spent only in verbose runs (-v) or when MLH_CHECK_FLUX_SYMMETRY is set
+    if (!(LOGCFG.level <= DEBUG || envInt("MLH_CHECK_FLUX_SYMMETRY", 0))) return;
+    int r[4] = {0, 0, 0, 0};
+    if (mlh_debug_fetch(gpu, "flux_symmetry", r, 4) != 4) return;
+    if (r[1] > 0) Logger(WARN) << "  > Fluxes are NOT symmetric for " << r[1] << " list slots (slot -> face map inconsistent)";
+#if PERIODIC_BOUNDARIES
+    if (r[3] > 0 && !mgpu::active())
+        Logger(WARN) << "  > Ghosts: " << r[3] << " one-sided periodic pairs (the reference's fluxes are NOT symmetric there)";
+#endif
+}
 
 void Particles::updateStateAndPosition(const double &dt, const Domain &) {
     ensure(PH_GRADIENTS);
