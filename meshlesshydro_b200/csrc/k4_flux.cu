@@ -143,15 +143,29 @@ __device__ __forceinline__ void rs_eval2(const RsConsts &c, double rhoL, double 
 }
 
 __device__ __forceinline__ double rs_gb(const RsConsts &c, double rho, double P, double Pstar) {
-    double A = c.tdgp1 / rho;
-    double B = c.gm1dgp1 * P;
-    return sqrt(A / (Pstar + B));
+    // sqrt(A / (Pstar + B)), A = 2/((g+1) rho), B = (g-1)/(g+1) P, as one rsqrt (the form rs_eval2 uses)
+    return c.sqrt_tdgp1 * rsqrt(rho * (Pstar + c.gm1dgp1 * P));
 }
 
+// x^(2 gamma/(gamma-1)) = x^n for the gammas whose (gamma-1)/(2 gamma) is 1/n (n = 5: 5/3, n = 7: 7/5)
+__device__ __forceinline__ double rs_int_pow(int n, double x) {
+    const double x2 = x * x, x4 = x2 * x2;
+    return n == 5 ? x4 * x : x4 * x2 * x;
+}
+
+// Toro's two-rarefaction / two-shock guesses (4.46, 4.48).  In smooth flow nearly EVERY face comes here (the PVRS value
+// falls outside [Pmin, Pmax] as soon as |du| exceeds the pressure jump), half of them into each branch: with the generic
+// pow = exp(y log x) this function was 45 % of k_face_setup's instructions on KH (3 pow calls of ~130 instructions at
+// 14 of 32 lanes, profiles/r2i_setup_lines_kh1000j.txt).  For gamma = 5/3 and 7/5 the exponents are 1/n and n:
+// two n-th roots (rs_root_pow) and an integer power instead.
 __device__ __noinline__ double rs_guess_nonlinear(const RsConsts c, double rhoL, double uL, double PL, double aL, double rhoR,
                                                   double uR, double PR, double aR, double Ppv, double Pmin) {
-    if (Ppv < Pmin) // two rarefactions
-        return mlh_pow((aL + aR - c.gm1d2 * (uR - uL)) / (aL / mlh_pow(PL, c.gm1d2g) + aR / mlh_pow(PR, c.gm1d2g)), c.tgdgm1);
+    if (Ppv < Pmin) { // two rarefactions
+        const double num = aL + aR - c.gm1d2 * (uR - uL);
+        if (c.root_n != 0 && PL > 1e-30 && PL < 1e30 && PR > 1e-30 && PR < 1e30)
+            return rs_int_pow(c.root_n, num / (aL / rs_root_pow<false>(c, PL) + aR / rs_root_pow<false>(c, PR)));
+        return mlh_pow(num / (aL / mlh_pow(PL, c.gm1d2g) + aR / mlh_pow(PR, c.gm1d2g)), c.tgdgm1);
+    }
     double gL = rs_gb(c, rhoL, PL, Ppv); // two shocks
     double gR = rs_gb(c, rhoR, PR, Ppv);
     return (gL * PL + gR * PR - uR + uL) / (gL + gR);
@@ -524,7 +538,11 @@ __device__ __forceinline__ void face_frame(const double *A, FaceFrame<D> &fr) {
     double n2 = 0.;
 #pragma unroll
     for (int k = 0; k < D; ++k) n2 += A[k] * A[k];
+#ifdef MLH_FRAME_RSQRT
+    const double inv = rsqrt(n2);
+#else
     const double inv = 1. / sqrt(n2);
+#endif
     if (D == 2) {
         fr.L[0] = inv * A[0];
         fr.L[1] = inv * A[1];
@@ -859,9 +877,13 @@ __device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid
 // ---------------------------------------------------------------------------------------------
 // resident blocks per SM (register cap): 3D needs 168 registers to run spill-free (3 blocks: 0.360 -> 0.339 ms at 61^3),
 // 2D fits 128 and gains from the fourth block (KH 1M 0.86 ms vs 1.04 ms at 3) -- A/B r01v, profiles/README.md
-#ifndef MLH_K4A_BLOCKS_PER_SM
-#define MLH_K4A_BLOCKS_PER_SM(D) ((D) == 3 ? 3 : 4)
+#ifndef MLH_K4A_BLOCKS_2D
+#define MLH_K4A_BLOCKS_2D 4
 #endif
+#ifndef MLH_K4A_BLOCKS_3D
+#define MLH_K4A_BLOCKS_3D 3
+#endif
+#define MLH_K4A_BLOCKS_PER_SM(D) ((D) == 3 ? MLH_K4A_BLOCKS_3D : MLH_K4A_BLOCKS_2D)
 #ifndef MLH_FUSE_SETUP
 #define MLH_FUSE_SETUP 0
 #endif
