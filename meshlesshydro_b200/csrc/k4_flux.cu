@@ -59,6 +59,17 @@ __device__ __forceinline__ double rs_min(double a, double b) { return (b < a) ? 
 
 __device__ __noinline__ double mlh_pow(double x, double y) { return x == 0. ? 0. : exp(y * log(x)); }
 
+// 1/x for normal positive x: MUFU.RCP64H estimate + two Newton steps
+__device__ __forceinline__ double rs_rcp(double x) {
+    if (!(x > 1e-300 && x < 1e300)) return 1. / x;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.);
+    return fma(y, e, y);
+}
+
 // x^((gamma-1)/(2 gamma)), the one power the root finder evaluates every iteration.  For gamma = 5/3 and 7/5 the
 // exponent is 1/5 resp. 1/7: z ~ x^(-1/n) from a single-precision seed (relative error e < 1e-6), residual
 // r = 1 - x z^n, and ONE third-order correction z <- z (1 + r/n + (n+1)/(2 n^2) r^2) -- the first terms of
@@ -1310,8 +1321,12 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_i
                 const int slot = (head + rank) & (MLH_RING - 1);
                 q.rhoL = rd[0][slot]; q.PL = rd[1][slot]; q.aL = rd[2][slot]; q.rhoR = rd[3][slot]; q.PR = rd[4][slot];
                 q.aR = rd[5][slot]; q.du = rd[6][slot];
-                q.iPL = 1. / q.PL;
-                q.iPR = 1. / q.PR;
+                // reciprocals by two Newton steps from the hardware estimate (<= 1 ulp; 6 instructions instead of the ~25 of
+                // an IEEE division -- this refill runs with ~5 of 32 lanes and the two divisions were 5 % of the kernel's
+                // warp instructions on KH, profiles/r2k_iterate_lines_kh1000j.txt).  Both code paths of the iteration use
+                // the same iPL / iPR, so results stay independent of the queue order.
+                q.iPL = rs_rcp(q.PL);
+                q.iPR = rs_rcp(q.PR);
                 const double v0 = rd[7][slot], v1 = rd[8][slot], v2 = rd[9][slot], v3 = rd[10][slot];
                 face = ri[slot];
                 const bool nw = rk[slot] == RS_NEWTON;
