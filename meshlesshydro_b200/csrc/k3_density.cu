@@ -199,13 +199,13 @@ int mlh_launch_density(mlh_ctx *c) {
     int n = p.own_end - p.own_begin;
     mlh_prof_begin(c, KID_DENSITY);
     if (p.D == 2 && p.periodic)
-        k_density_matrix<2, true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+        k_density_matrix<2, true><<<mlh_blocks(n > 0 ? n : 1, 128), 128, 0, c->stream>>>(p);
     else if (p.D == 2)
-        k_density_matrix<2, false><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+        k_density_matrix<2, false><<<mlh_blocks(n > 0 ? n : 1, 128), 128, 0, c->stream>>>(p);
     else if (p.periodic)
-        k_density_matrix<3, true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+        k_density_matrix<3, true><<<mlh_blocks(n > 0 ? n : 1, 128), 128, 0, c->stream>>>(p);
     else
-        k_density_matrix<3, false><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+        k_density_matrix<3, false><<<mlh_blocks(n > 0 ? n : 1, 128), 128, 0, c->stream>>>(p);
     mlh_prof_end(c, KID_DENSITY);
     MLH_CUDA_CHECK(c, cudaGetLastError());
     return MLH_OK;

@@ -231,13 +231,13 @@ int mlh_launch_gradient(mlh_ctx *c) {
     // the dt accumulator was set to DBL_MAX (Particles.cpp:1447) by k_density_matrix
     mlh_prof_begin(c, KID_GRADIENT);
     if (p.D == 2 && p.periodic)
-        k_gradient_limit<2, true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+        k_gradient_limit<2, true><<<mlh_blocks(n > 0 ? n : 1, 128), 128, 0, c->stream>>>(p);
     else if (p.D == 2)
-        k_gradient_limit<2, false><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+        k_gradient_limit<2, false><<<mlh_blocks(n > 0 ? n : 1, 128), 128, 0, c->stream>>>(p);
     else if (p.periodic)
-        k_gradient_limit<3, true><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+        k_gradient_limit<3, true><<<mlh_blocks(n > 0 ? n : 1, 128), 128, 0, c->stream>>>(p);
     else
-        k_gradient_limit<3, false><<<mlh_blocks(n, 128), 128, 0, c->stream>>>(p);
+        k_gradient_limit<3, false><<<mlh_blocks(n > 0 ? n : 1, 128), 128, 0, c->stream>>>(p);
     mlh_prof_end(c, KID_GRADIENT);
     MLH_CUDA_CHECK(c, cudaGetLastError());
     return MLH_OK;
