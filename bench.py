@@ -386,7 +386,7 @@ def rooflines(res, local_rank):
         "k4a_face_states": lambda: n_local * (2 * D + 4 + D * D + (D + 2) * D) * 8 + nfaces * ((4 * D + 4) * 8 + 8),
         "k4c_flux_sum_update": lambda: nslots * (4 + frec * 8) + n_local * 2 * (2 * D + 2) * 8,
         "k2b_face_index": lambda: nslots * 12 + nfaces * 8,
-        "k4b1_face_setup": lambda: nfaces * (6 * 8 + 11 * 8 + 4),
+        "k4b1_face_setup": lambda: nfaces * (6 * 8 + 12 * 8 + 4),
         "k4b3_face_finish": lambda: nfaces * ((4 * D + 4) * 8 + 8 + frec * 8),
     }
     roofline = {"kernel": top, "share_of_step": prof[top][0] / psteps / step_ms_prof if step_ms_prof else None,

@@ -199,14 +199,29 @@ struct RsProblem {
 enum { RS_DONE = 0, RS_NEWTON = 1, RS_BRENT = 2 };
 struct RsIter {
     double a, b, c, d, fa, fb, fc;
+    double fpb; // Brent: f' at the upper end of the bracket it started from = lower bound of f' on the bracket (f is concave)
     int method, mflag;
 };
 
+// Early exit of Brent's method, exact to 2e-13 relative.  f(P) = f_L + f_R + du is increasing and CONCAVE (Toro 4.3.1), so on
+// a bracket [a, b] that started at an upper end U: f'(x) >= f'(U) = fpb for every x <= U.  If the best point b is the upper
+// end and 0 < f(b) <= 1e-13 b fpb, the root lies in [b (1 - 1e-13), b], and everything the reference's iteration can still
+// return -- a later b has |f| <= f(b), hence lies within f(b)/fpb of the root -- lies in [b (1 - 2e-13), b].  The reference
+// (RiemannSolver::solve, restated in oracle/riemann_exact.h) spends 27-29 further bisections on exactly these faces: its
+// interpolation steps collapse onto b and the lower end creeps up from 0 by halving until |a - b| < 5e-9 (a + b).
+// CPU study on the oracle's faces (3 steps in): the rule fires on 56 % / 57 % / 30 % of the faces of KH / Sedov / fluid block
+// and removes 75 % / 35 % / 65 % of ALL root-finder iterations; largest deviation of P* from the reference's value 1.0e-13.
+#define MLH_BRENT_CERTAIN 1e-13
+__device__ __forceinline__ bool rs_brent_certain(const RsIter &it) {
+    return (it.b > it.a) & (it.fb > 0.) & (it.fb <= MLH_BRENT_CERTAIN * it.b * it.fpb);
+}
+
 // enter Brent on [lower, upper]; returns false if it terminates immediately (result in it.b)
-__device__ __forceinline__ bool rs_brent_begin(RsIter &it, double lower, double upper, double lowf, double upf) {
+__device__ __forceinline__ bool rs_brent_begin(RsIter &it, double lower, double upper, double lowf, double upf, double fp_upper) {
     double a = lower, b = upper, fa = lowf, fb = upf;
     it.method = RS_DONE;
     it.b = b;
+    it.fpb = fp_upper;
     if (fa * fb > 0.) return false; // not bracketed: keep upper (as the oracle)
     if (fabs(fa) < fabs(fb)) {
         double t = a; a = b; b = t;
@@ -214,7 +229,7 @@ __device__ __forceinline__ bool rs_brent_begin(RsIter &it, double lower, double 
     }
     it.a = a; it.b = b; it.fa = fa; it.fb = fb;
     it.c = a; it.fc = fa; it.d = 1e230; it.mflag = 1;
-    if (!(fb == 0.) && (fabs(a - b) > 5.e-9 * (a + b))) {
+    if (!(fb == 0.) && (fabs(a - b) > 5.e-9 * (a + b)) && !rs_brent_certain(it)) {
         it.method = RS_BRENT;
         return true;
     }
@@ -228,13 +243,14 @@ __device__ __forceinline__ void rs_iter_begin(const RsProblem &q, RsIter &it) {
     it.mflag = 0;
     it.b = Pguess;
     it.a = Pstar; it.fa = fPstar; it.fb = fPguess; it.c = q.fpsum; it.d = 0.; it.fc = 0.;
+    it.fpb = q.fpsum;
     if (fPstar * fPguess >= 0.) {
         if (fabs(Pstar - Pguess) > 5.e-9 * (Pstar + Pguess) && fPguess < 0.) {
             it.method = RS_NEWTON;
             return;
         }
     }
-    if (1.e6 * fabs(Pstar - Pguess) > 0.5 * (Pstar + Pguess) && fPguess > 0.) rs_brent_begin(it, Pstar, Pguess, fPstar, fPguess);
+    if (1.e6 * fabs(Pstar - Pguess) > 0.5 * (Pstar + Pguess) && fPguess > 0.) rs_brent_begin(it, Pstar, Pguess, fPstar, fPguess, q.fpsum);
 }
 
 // trial pressure of this iteration
@@ -274,7 +290,7 @@ __device__ __forceinline__ void rs_iter_update(RsIter &it, double s, double fs, 
         const double Pstar = it.a, Pguess = it.b;
         if (fabs(Pstar - Pguess) > 5.e-9 * (Pstar + Pguess) && fs < 0.) return; // next Newton iteration
         it.method = RS_DONE;
-        if (1.e6 * fabs(Pstar - Pguess) > 0.5 * (Pstar + Pguess) && fs > 0.) rs_brent_begin(it, Pstar, Pguess, it.fa, fs);
+        if (1.e6 * fabs(Pstar - Pguess) > 0.5 * (Pstar + Pguess) && fs > 0.) rs_brent_begin(it, Pstar, Pguess, it.fa, fs, fps);
         return;
     }
     double a = it.a, b = it.b, fa = it.fa, fb = it.fb;
@@ -293,7 +309,7 @@ __device__ __forceinline__ void rs_iter_update(RsIter &it, double s, double fs, 
         t = fa; fa = fb; fb = t;
     }
     it.a = a; it.b = b; it.fa = fa; it.fb = fb;
-    if (!(!(fb == 0.) && (fabs(a - b) > 5.e-9 * (a + b)))) it.method = RS_DONE;
+    if (!(!(fb == 0.) && (fabs(a - b) > 5.e-9 * (a + b))) || rs_brent_certain(it)) it.method = RS_DONE;
 }
 
 // f_L(Ps) + f_R(Ps) + du without branches: both sides evaluate the rarefaction AND the shock expression (same
@@ -339,7 +355,7 @@ __device__ __forceinline__ void rs_brent_step(const RsConsts &cst, const RsProbl
     it.fa = sw ? nfb : nfa;
     it.b = sw ? na : nb;
     it.fb = sw ? nfa : nfb;
-    if (!(!(it.fb == 0.) && (fabs(it.a - it.b) > 5.e-9 * (it.a + it.b)))) it.method = RS_DONE;
+    if (!(!(it.fb == 0.) && (fabs(it.a - it.b) > 5.e-9 * (it.a + it.b))) || rs_brent_certain(it)) it.method = RS_DONE;
 }
 
 // vacuum sampling (Toro 4.6); cold path
@@ -825,12 +841,12 @@ __device__ __forceinline__ void face_load(const double *rec, size_t fs, double *
 }
 
 // queue layout (chunk-sized, SoA): qd[k * cstride + q], k = 0..6 problem (rhoL, PL, aL, rhoR, PR, aR, du), 7..10 start of
-// the root finder (Pguess, f(Pguess), f(0), f'(Pguess)); qi[q] = face index relative to the chunk.  Faces that start
+// the root finder (Pguess, f(Pguess), f(0), f'(Pguess)), 11 = f' bound of the bracket (rs_brent_certain); qi[q] = face index relative to the chunk.  Faces that start
 // with Newton-Raphson are appended from the front (q = 0, 1, ..), faces that start with Brent from the back
 // (q = cstride-1, cstride-2, ..), so that the warps of k_face_iterate work on one kind at a time.  To keep the
 // append counters from serialising (one L2 atomic per warp and kind), the queue is split into MLH_Q_REGIONS regions
 // of equal capacity with their own pair of counters; the warp-tile of 32 faces number t appends to region t % REGIONS.
-#define MLH_Q_FIELDS 11
+#define MLH_Q_FIELDS 12
 #define MLH_Q_REGIONS 128
 __host__ __device__ __forceinline__ int q_region_cap(int cstride) { // faces per region (multiple of 32)
     const int nwt = (cstride + 31) / 32;
@@ -878,6 +894,7 @@ __device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid
             d[8 * qs] = it.b;
             d[9 * qs] = kind == RS_NEWTON ? it.fb : it.fa;
             d[10 * qs] = kind == RS_NEWTON ? it.c : it.fb;
+            d[11 * qs] = it.fpb;
             qi[at] = fl;
         }
     }
@@ -1277,7 +1294,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_i
     RsIter it;
     it.method = RS_DONE;
     it.mflag = 0;
-    it.a = it.b = it.c = it.d = it.fa = it.fb = it.fc = 0.;
+    it.a = it.b = it.c = it.d = it.fa = it.fb = it.fc = it.fpb = 0.;
     for (;;) {
         // ---- prefetch the next batch while at most half of the ring is occupied ----
         if (pend == 0 && avail <= MLH_RING - 32 && bq < NB) {
@@ -1328,6 +1345,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_i
                 q.iPL = rs_rcp(q.PL);
                 q.iPR = rs_rcp(q.PR);
                 const double v0 = rd[7][slot], v1 = rd[8][slot], v2 = rd[9][slot], v3 = rd[10][slot];
+                it.fpb = rd[11][slot];
                 face = ri[slot];
                 const bool nw = rk[slot] == RS_NEWTON;
                 it.method = nw ? RS_NEWTON : RS_BRENT;

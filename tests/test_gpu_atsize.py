@@ -84,7 +84,7 @@ def test_chunked_flux_pass_is_bitwise_identical(case, stage_bytes):
         states.append((dts, gpu.download_state(), gpu.error_flags()))
         gpu.close()
     D = ic["dim"]
-    per_face = (4 * D + 4 + 1 + 11) * 8 + 4  # record + P* + solver queue entry (mlh_stage_alloc)
+    per_face = (4 * D + 4 + 1 + 12) * 8 + 4  # record + P* + solver queue entry (mlh_stage_alloc)
     assert nfaces * per_face >= 3 * stage_bytes, "the small budget must force >= 3 chunks (%d faces)" % nfaces
     assert states[0][2] == states[1][2], "device flags differ between one chunk and many"
     assert states[0][0] == states[1][0], "dt differs between one chunk and many"
