@@ -1610,21 +1610,26 @@ int mlh_launch_face_index(mlh_ctx *c) {
 int mlh_stage_alloc(mlh_ctx *c) {
     Params &p = c->p;
     const size_t per_face = (size_t)(4 * p.D + 4 + 1 + MLH_Q_FIELDS) * sizeof(double) + sizeof(int);
-    size_t budget = (size_t)6 << 30;
-    if (c->cfg.stage_bytes > 0) {
-        budget = (size_t)c->cfg.stage_bytes;
-    } else {
-        // default: an eighth of the device memory (22 GB of B200's 180 GB: KH 4 M = 95 M faces in one chunk), at most a
-        // third of what is free right now, never below 1 GiB
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            budget = total_b / 8;
-            if (budget > free_b / 3) budget = free_b / 3;
-            if (budget < ((size_t)1 << 30)) budget = (size_t)1 << 30;
+    // budget: mlh_config.stage_bytes, else an eighth of the device memory (22 GB of B200's 180 GB: KH 4 M = 95 M faces in
+    // one chunk), at most a third of what was free when first asked, never below 1 GiB.  Asked ONCE per context:
+    // cudaMemGetInfo costs milliseconds of host time (it stalled every step of the small workloads, visit r2z).
+    if (c->stage_budget == 0) {
+        size_t budget0 = (size_t)6 << 30;
+        if (c->cfg.stage_bytes > 0) {
+            budget0 = (size_t)c->cfg.stage_bytes;
         } else {
-            cudaGetLastError();
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                budget0 = total_b / 8;
+                if (budget0 > free_b / 3) budget0 = free_b / 3;
+                if (budget0 < ((size_t)1 << 30)) budget0 = (size_t)1 << 30;
+            } else {
+                cudaGetLastError();
+            }
         }
+        c->stage_budget = budget0;
     }
+    const size_t budget = c->stage_budget;
     long chunk = (long)(budget / per_face);
     chunk = chunk / MLH_FACE_TILE * MLH_FACE_TILE;
     if (chunk < 4 * MLH_FACE_TILE) chunk = 4 * MLH_FACE_TILE;

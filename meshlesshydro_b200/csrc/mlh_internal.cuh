@@ -319,6 +319,7 @@ struct mlh_ctx {
     size_t pool_bytes;
     double *stage;       // face staging buffer of K4 (k4_flux.cu): record, P*, solver queue x stage_chunk
     int stage_chunk;     // faces per K4 chunk (multiple of 128)
+    size_t stage_budget; // bytes the staging buffer may take (fixed at the first flux pass)
     int num_sms;
     double *dl_scratch;  // un-permutation staging of mlh_download_state / mlh_download_diag (8 x ncap doubles, lazily allocated)
     char *rf_buf;        // device scratch of mlh_riemann_faces (the reference's per-face Riemann class: kept between calls)
