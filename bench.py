@@ -481,20 +481,55 @@ def main():
         return 0
 
     # ---------------- B200 arm ----------------
-    # a rank that fails must not leave the others waiting in an NCCL call until the launcher's timeout: leave at once
-    # (torchrun then stops the peers); and no run may sit for more than 25 minutes whatever happens
-    import signal
+    # A rank that fails must not leave the others waiting in an NCCL call until the launcher's timeout, and no run may
+    # sit for more than 25 minutes whatever happens.  The watchdog is a THREAD: a Python signal handler cannot run
+    # while the main thread is inside a C call (a blocked ncclAllReduce / cudaStreamSynchronize), a thread can.
+    # Once the main workload has been measured its JSON line is parked in `pending`; if one of the optional sections
+    # after it (the Sedov 256^3 run at N=8, the sharded-vs-single check) hangs or fails, rank 0 still prints that line,
+    # with the section's error recorded in it.
+    import threading
+    import time
     import traceback
 
-    def _bail(*_):
-        sys.stderr.write("bench.py: watchdog / failure on rank %d\n" % rank)
-        traceback.print_stack()
-        os._exit(3)
-    signal.signal(signal.SIGALRM, _bail)
-    signal.alarm(1500)
-    # exactly ONE line may reach stdout; libraries (NCCL prints its version banner there) are sent to stderr
     json_fd = os.dup(1)
-    os.dup2(2, 1)
+    os.dup2(2, 1)  # exactly ONE line may reach stdout; libraries (NCCL prints its version banner there) go to stderr
+    state = {"deadline": time.time() + 1500.0, "pending": None, "section": "main", "done": False}
+    lock = threading.Lock()
+
+    def _emit_and_exit(why, code):
+        with lock:
+            if state["done"]:
+                return
+            state["done"] = True
+            line = state["pending"]
+        sys.stderr.write("bench.py: rank %d leaves in section '%s': %s\n" % (rank, state["section"], why))
+        if line is not None:
+            if rank == 0:
+                line[state["section"]] = {"error": why}
+                os.write(json_fd, (json.dumps(line) + "\n").encode())
+            os._exit(0)
+        os._exit(code)
+
+    def _watch():
+        while True:
+            time.sleep(1.0)
+            if state["done"]:
+                return
+            if time.time() > state["deadline"]:
+                _emit_and_exit("watchdog: no progress within the section's time limit", 3)
+    threading.Thread(target=_watch, daemon=True).start()
+
+    def _enter(section, limit):
+        """start an optional section; MLH_BENCH_FAULT=section:raise|hang:rank and MLH_BENCH_SECTION_LIMIT=seconds exist
+        so that the way out of a one-rank failure can be exercised on real GPUs (tools/visit_mgpu_final.sh)"""
+        state["section"] = section
+        state["deadline"] = time.time() + float(os.environ.get("MLH_BENCH_SECTION_LIMIT", limit))
+        fault = os.environ.get("MLH_BENCH_FAULT", "").split(":")
+        if len(fault) == 3 and fault[0] == section and int(fault[2]) == rank:
+            if fault[1] == "raise":
+                raise RuntimeError("injected fault in section " + section)
+            time.sleep(1e6)
+
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -506,40 +541,59 @@ def main():
         res = run_workload(args, wname, dist, rank, world, local_rank, want_profile=True, want_e2e=not args.no_e2e)
     except Exception:
         traceback.print_exc()
-        os._exit(2)
+        _emit_and_exit("exception in the main workload", 2)
     res["world"] = world
-    also = None
+    D, n_local = res["D"], res["n_local"]
+    roofline, kernel_rooflines, hbm, kernels = rooflines(res, local_rank) if rank == 0 else (None, None, None, None)
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": res["wdesc"], "n_particles": res["n_total"], "dim": D, "mean_neighbours": res["noi_mean"],
+                       "kernel_size": res["h"], "abs_mode": "INT_TRUNC (g++/libstdc++ build of the reference)",
+                       "l2": "no flush between steps; per-step working set %.0f MB vs 126 MB L2"
+                             % (n_local * (ALL_ALGO_BYTES[D] + 4 * (res["noi_mean"] or 32) * 4) / 1e6),
+                       "parallelism": "slab%d" % world if world > 1 else "single"},
+            "timed_region": res["timed_region"], "clocks": res["clocks"], "e2e": res.get("e2e"),
+            "gpu_launches": res["launches"], "gpu_launches_per_step": res["launches"] / float(res["timed_region"]["steps_total"]),
+            "roofline": roofline, "hbm_view": hbm, "kernel_rooflines": kernel_rooflines, "num_faces": res["nfaces"],
+            "kernels": kernels, "cpu_baseline": None, "device_flags": res["flags"], "also": None, "mgpu_check": None}
+    with lock:
+        state["pending"] = line
+
     if world == 8 and args.workload is None and not args.no_also:
         # BASELINE configs[4]: Sedov 3D 256^3 = 16.7 M particles, halo exchange across 8 x B200
-        a = run_workload(args, "sedov256", dist, rank, world, local_rank, want_profile=False, want_e2e=False)
-        also = {"sedov256": {"workload": a["wdesc"], "n_particles": a["n_total"], "value": a["value"], "unit": UNIT,
-                             "ms_per_step": a["ms_per_step"], "timed_region": a["timed_region"], "n_gpus": world,
-                             "device_flags": a["flags"]}}
-    check = None
+        try:
+            _enter("also", 420.0)
+            a = run_workload(args, "sedov256", dist, rank, world, local_rank, want_profile=False, want_e2e=False)
+            line["also"] = {"sedov256": {"workload": a["wdesc"], "n_particles": a["n_total"], "value": a["value"], "unit": UNIT,
+                                         "ms_per_step": a["ms_per_step"], "timed_region": a["timed_region"], "n_gpus": world,
+                                         "device_flags": a["flags"]}}
+        except Exception:
+            traceback.print_exc()
+            _emit_and_exit("exception", 0)
     if world > 1 and not args.no_check:
-        check = mgpu_bitwise_check(dist, local_rank, rank, world)
-    cpu = None
+        try:
+            _enter("mgpu_check", 300.0)
+            line["mgpu_check"] = mgpu_bitwise_check(dist, local_rank, rank, world)
+        except Exception:
+            traceback.print_exc()
+            _emit_and_exit("exception", 0)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _enter("cpu_baseline", 400.0)
         cpu = time_reference(factory, preset, CPU_SIDES[wname], 2, 1, budget_s=25.0)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    with lock:
+        state["done"] = True
     if rank == 0:
-        D, n_local = res["D"], res["n_local"]
-        roofline, kernel_rooflines, hbm, kernels = rooflines(res, local_rank)
-        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": res["wdesc"], "n_particles": res["n_total"], "dim": D, "mean_neighbours": res["noi_mean"],
-                           "kernel_size": res["h"], "abs_mode": "INT_TRUNC (g++/libstdc++ build of the reference)",
-                           "l2": "no flush between steps; per-step working set %.0f MB vs 126 MB L2"
-                                 % (n_local * (ALL_ALGO_BYTES[D] + 4 * (res["noi_mean"] or 32) * 4) / 1e6),
-                           "parallelism": "slab%d" % world if world > 1 else "single"},
-                "timed_region": res["timed_region"], "clocks": res["clocks"], "e2e": res.get("e2e"),
-                "gpu_launches": res["launches"], "gpu_launches_per_step": res["launches"] / float(res["timed_region"]["steps_total"]),
-                "roofline": roofline, "hbm_view": hbm, "kernel_rooflines": kernel_rooflines, "num_faces": res["nfaces"],
-                "kernels": kernels, "cpu_baseline": cpu, "device_flags": res["flags"], "also": also, "mgpu_check": check}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
-        dist.destroy_process_group()
+        state["done"] = False
+        state["pending"], state["section"], state["deadline"] = None, "shutdown", time.time() + 60.0
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        state["done"] = True
     return 0
 
 
