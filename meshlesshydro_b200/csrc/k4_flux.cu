@@ -1556,6 +1556,9 @@ int launch_chunks(mlh_ctx *c, double dt_fixed, double dt_max) {
     static const int g_finish = getenv("MLH_GRID_FINISH") ? atoi(getenv("MLH_GRID_FINISH")) : 2 * MLH_FINISH_BLOCKS;
     // K4a: two clean waves of its resident blocks (3 per SM in 3D, 4 in 2D): 0.339 -> 0.309 ms at 61^3 (r01w)
     static const int g_states = getenv("MLH_GRID_STATES") ? atoi(getenv("MLH_GRID_STATES")) : 2 * MLH_K4A_BLOCKS_PER_SM(D);
+    // Riemann iteration: resident blocks per SM it is launched with (a smaller grid leaves room for kernels of another
+    // stream, tools/overlap_probe.py)
+    static const int g_iter = getenv("MLH_GRID_ITERATE") ? max(1, min(MLH_K4B_BLOCKS_PER_SM, atoi(getenv("MLH_GRID_ITERATE")))) : MLH_K4B_BLOCKS_PER_SM;
     cudaStream_t st = c->stream;
     // The face count lives on the device (face_start[own_end]); without a host round trip the chunk loop covers the
     // face CAPACITY and the kernels of chunks beyond the last face return at once.  One chunk in the usual case.
@@ -1575,7 +1578,7 @@ int launch_chunks(mlh_ctx *c, double dt_fixed, double dt_max) {
             mlh_prof_end(c, KID_FLUX_SETUP);
         }
         mlh_prof_begin(c, KID_FLUX);
-        k_face_iterate<<<c->num_sms * MLH_K4B_BLOCKS_PER_SM, MLH_FACE_TILE, 0, st>>>(p, pstar, qd, qi, qcount, chunk);
+        k_face_iterate<<<c->num_sms * g_iter, MLH_FACE_TILE, 0, st>>>(p, pstar, qd, qi, qcount, chunk);
         mlh_prof_end(c, KID_FLUX);
         mlh_prof_begin(c, KID_FLUX_FINISH);
         k_face_finish<D><<<c->num_sms * g_finish, MLH_FACE_TILE, 0, st>>>(p, c->stage, pstar, (int)f0, chunk);
