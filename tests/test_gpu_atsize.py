@@ -5,11 +5,15 @@
   oracle/ref_build/Makefile with MAX_NUM_INTERACTIONS 128), one full step: ~4 s of CPU per pass.
 * BASELINE configs[2], fluid block 2D N = 1000^2: against oracle/liboracle.so (the C restatement, itself pinned
   bit for bit to the reference sources by tests/test_oracle_vs_ref.py) with 64 slots per particle: ~25 s per pass.
+* Kelvin-Helmholtz 2D periodic N = 1000^2 against the oracle (~1 min); BASELINE configs[3], N = 2000^2 = the default
+  bench workload, behind MLH_ATSIZE_KH2000=1 (~6 min of CPU).
 
 Bars: cell ids and ordered neighbour lists bit-exact; omega, rho, P, x, m, u per-particle relative <= 1e-10;
 gradients, flux sums, velocities <= 1e-10 under the scaled rule (tests/parity.py); per-face A_ij, W_L/W_R, F_ij
 (Particles.cpp:1290-1911) <= 1e-10 at Sedov 61^3.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -70,6 +74,31 @@ def test_fluid_block_1000_squared_vs_oracle():
     print("fluid block 1000^2 vs oracle:", {k: ("%.1e" % v if isinstance(v, float) else v) for k, v in worst.items()})
     gpu.close()
     orc.close()
+
+
+def _kh_at_size(side):
+    ic = IC.kelvin_helmholtz(side, lattice=True, jitter=0.2)  # the generator bench.py uses for kh1000 / kh2000
+    ocfg = orc_config("kh2d", ic["h"], ic["gamma"], ic.get("box"), abs_mode=0, max_ni=96, max_gi=96)
+    orc = Oracle(ocfg, ic)
+    cfg = capi.make_config("kh2d", ic["h"], ic["gamma"], ic.get("box"), abs_mode=capi.ABS_INT_TRUNC, debug_capture=1,
+                           max_interactions=96)
+    gpu = capi.MfvGpu(cfg)
+    gpu.upload(ic)
+    worst = _one_step(ic, orc, gpu, faces=False)
+    print("KH %d^2 (periodic) vs oracle:" % side, {k: ("%.1e" % v if isinstance(v, float) else v) for k, v in worst.items()})
+    gpu.close()
+    orc.close()
+
+
+def test_kelvin_helmholtz_1000_squared_vs_oracle():
+    """periodic 2D at 1 M particles: ghost lists, images and the seam at size (~1 min of CPU for the oracle)"""
+    _kh_at_size(1000)
+
+
+@pytest.mark.skipif(not os.environ.get("MLH_ATSIZE_KH2000"), reason="BASELINE configs[3] = bench.py's default workload, "
+                    "one step against the oracle: ~6 min of CPU; set MLH_ATSIZE_KH2000=1 (log of the last run: profiles/)")
+def test_kelvin_helmholtz_2000_squared_vs_oracle():
+    _kh_at_size(2000)
 
 
 # ---- the chunked flux pass (launch_chunks, csrc/k4_flux.cu): C4 on one GPU and C5 on eight run 2-8 staging chunks per
