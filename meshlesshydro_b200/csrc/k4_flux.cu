@@ -687,6 +687,20 @@ __device__ __forceinline__ int w2f(int nu) { return nu == 0 ? 0 : (nu == 1 ? 4 :
 // stage[k * cstride + f]) so that K4a's stores and K4b's loads are coalesced.
 //   [0..5] rhoL PL uL rhoR PR uR   (L = canonical endpoint a, u = velocity along the face normal)
 //   [6..]  transverse velocities of a (D-1), of b (D-1), vFrame (D), A_ij (D)
+// Staging traffic is written once and read once or twice by later kernels, never re-used from L2 before it is evicted
+// (a chunk's record alone is several times the 126 MB L2).  Streaming (evict-first) accesses for it, so that it does
+// not displace the pk1/pk2 records and F that ARE gathered repeatedly, changed nothing or LOST (A/B r2v, Sedov 61^3 /
+// KH 1M / KH 4M: setup 0.142 -> 0.144, 0.995 -> 1.026, 3.97 -> 4.13 ms, every other kernel within 1 %): off
+#ifndef MLH_STREAM_HINTS
+#define MLH_STREAM_HINTS 0
+#endif
+#if MLH_STREAM_HINTS
+#define MLH_ST_STAGE(ptr, val) __stcs((ptr), (val))
+#define MLH_LD_STAGE(ptr) __ldcs(ptr)
+#else
+#define MLH_ST_STAGE(ptr, val) (*(ptr) = (val))
+#define MLH_LD_STAGE(ptr) (*(ptr))
+#endif
 template <int D> struct FaceRec {
     static constexpr int NW = D + 2;
     static constexpr int RHOL = 0, PL = 1, UL = 2, RHOR = 3, PR = 4, UR = 5, VTA = 6, VTB = 6 + (D - 1), VF = 6 + 2 * (D - 1),
@@ -697,21 +711,21 @@ template <int D> struct FaceRec {
 template <int D>
 __device__ __forceinline__ void face_store(double *rec, size_t fs, const double *Wa, const double *Wb, const double *vF, const double *A) {
     using R = FaceRec<D>;
-    rec[R::RHOL * fs] = Wa[0];
-    rec[R::PL * fs] = Wa[1];
-    rec[R::UL * fs] = Wa[2];
-    rec[R::RHOR * fs] = Wb[0];
-    rec[R::PR * fs] = Wb[1];
-    rec[R::UR * fs] = Wb[2];
+    MLH_ST_STAGE(&rec[R::RHOL * fs], Wa[0]);
+    MLH_ST_STAGE(&rec[R::PL * fs], Wa[1]);
+    MLH_ST_STAGE(&rec[R::UL * fs], Wa[2]);
+    MLH_ST_STAGE(&rec[R::RHOR * fs], Wb[0]);
+    MLH_ST_STAGE(&rec[R::PR * fs], Wb[1]);
+    MLH_ST_STAGE(&rec[R::UR * fs], Wb[2]);
 #pragma unroll
     for (int k = 1; k < D; ++k) {
-        rec[(R::VTA + k - 1) * fs] = Wa[2 + k];
-        rec[(R::VTB + k - 1) * fs] = Wb[2 + k];
+        MLH_ST_STAGE(&rec[(R::VTA + k - 1) * fs], Wa[2 + k]);
+        MLH_ST_STAGE(&rec[(R::VTB + k - 1) * fs], Wb[2 + k]);
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        rec[(R::VF + k) * fs] = vF[k];
-        rec[(R::AA + k) * fs] = A[k];
+        MLH_ST_STAGE(&rec[(R::VF + k) * fs], vF[k]);
+        MLH_ST_STAGE(&rec[(R::AA + k) * fs], A[k]);
     }
 }
 
@@ -822,21 +836,21 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
 template <int D>
 __device__ __forceinline__ void face_load(const double *rec, size_t fs, double *Wa, double *Wb, double *vF, double *A) {
     using R = FaceRec<D>;
-    Wa[0] = rec[R::RHOL * fs];
-    Wa[1] = rec[R::PL * fs];
-    Wa[2] = rec[R::UL * fs];
-    Wb[0] = rec[R::RHOR * fs];
-    Wb[1] = rec[R::PR * fs];
-    Wb[2] = rec[R::UR * fs];
+    Wa[0] = MLH_LD_STAGE(&rec[R::RHOL * fs]);
+    Wa[1] = MLH_LD_STAGE(&rec[R::PL * fs]);
+    Wa[2] = MLH_LD_STAGE(&rec[R::UL * fs]);
+    Wb[0] = MLH_LD_STAGE(&rec[R::RHOR * fs]);
+    Wb[1] = MLH_LD_STAGE(&rec[R::PR * fs]);
+    Wb[2] = MLH_LD_STAGE(&rec[R::UR * fs]);
 #pragma unroll
     for (int k = 1; k < D; ++k) {
-        Wa[2 + k] = rec[(R::VTA + k - 1) * fs];
-        Wb[2 + k] = rec[(R::VTB + k - 1) * fs];
+        Wa[2 + k] = MLH_LD_STAGE(&rec[(R::VTA + k - 1) * fs]);
+        Wb[2 + k] = MLH_LD_STAGE(&rec[(R::VTB + k - 1) * fs]);
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        vF[k] = rec[(R::VF + k) * fs];
-        A[k] = rec[(R::AA + k) * fs];
+        vF[k] = MLH_LD_STAGE(&rec[(R::VF + k) * fs]);
+        A[k] = MLH_LD_STAGE(&rec[(R::AA + k) * fs]);
     }
 }
 
@@ -869,9 +883,9 @@ __device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid
         if (rs_setup(p.rs, rhoL, uL, PL, rhoR, uR, PR, q)) {
             rs_iter_begin(q, it);
             method = it.method;
-            if (method == RS_DONE) pstar[fl] = it.b;
+            if (method == RS_DONE) MLH_ST_STAGE(pstar + fl, it.b);
         } else {
-            pstar[fl] = MLH_PSTAR_VACUUM;
+            MLH_ST_STAGE(pstar + fl, MLH_PSTAR_VACUUM);
         }
     }
 #pragma unroll
@@ -888,14 +902,15 @@ __device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid
             at = region * rcap + (kind == RS_BRENT ? rcap - 1 - at : at);
             double *d = qd + at;
             const size_t qs = (size_t)MLH_Q_REGIONS * rcap; // field stride of the queue
-            d[0 * qs] = q.rhoL; d[1 * qs] = q.PL; d[2 * qs] = q.aL; d[3 * qs] = q.rhoR; d[4 * qs] = q.PR; d[5 * qs] = q.aR;
-            d[6 * qs] = q.du;
-            d[7 * qs] = kind == RS_NEWTON ? it.fa : it.a;
-            d[8 * qs] = it.b;
-            d[9 * qs] = kind == RS_NEWTON ? it.fb : it.fa;
-            d[10 * qs] = kind == RS_NEWTON ? it.c : it.fb;
-            d[11 * qs] = it.fpb;
-            qi[at] = fl;
+            MLH_ST_STAGE(d + 0 * qs, q.rhoL); MLH_ST_STAGE(d + 1 * qs, q.PL); MLH_ST_STAGE(d + 2 * qs, q.aL);
+            MLH_ST_STAGE(d + 3 * qs, q.rhoR); MLH_ST_STAGE(d + 4 * qs, q.PR); MLH_ST_STAGE(d + 5 * qs, q.aR);
+            MLH_ST_STAGE(d + 6 * qs, q.du);
+            MLH_ST_STAGE(d + 7 * qs, kind == RS_NEWTON ? it.fa : it.a);
+            MLH_ST_STAGE(d + 8 * qs, it.b);
+            MLH_ST_STAGE(d + 9 * qs, kind == RS_NEWTON ? it.fb : it.fa);
+            MLH_ST_STAGE(d + 10 * qs, kind == RS_NEWTON ? it.c : it.fb);
+            MLH_ST_STAGE(d + 11 * qs, it.fpb);
+            MLH_ST_STAGE(qi + at, fl);
         }
     }
 }
@@ -1228,7 +1243,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_SETUP_BLOCKS) k_face_setup(
         double w[6] = {1., 1., 0., 1., 1., 0.};
         if (valid) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) w[k] = stage[k * fs + fl];
+            for (int k = 0; k < 6; ++k) w[k] = MLH_LD_STAGE(stage + k * fs + fl);
         }
         face_setup_and_queue(p, valid, fl, w[R::RHOL], w[R::PL], w[R::UL], w[R::RHOR], w[R::PR], w[R::UR], pstar, qd, qi, qcount, rcap);
     }
@@ -1321,7 +1336,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4B_BLOCKS_PER_SM) k_face_i
         // ---- lanes whose face has converged store P* and take the next ring entry ----
         const bool done = it.method == RS_DONE;
         if (done && face >= 0) {
-            pstar[face] = it.b;
+            MLH_ST_STAGE(pstar + face, it.b);
             face = -1;
         }
         const unsigned need = __ballot_sync(0xffffffffu, done);
@@ -1400,7 +1415,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_FINISH_BLOCKS) k_face_finis
         FaceFrame<D> fr;
         face_load<D>(stage + (f - f0), fs, Wa, Wb, vF, A); // velocities already in the face frame (K4a)
         face_frame<D>(A, fr);
-        const double Ps = pstar[f - f0];
+        const double Ps = MLH_LD_STAGE(pstar + (f - f0));
         double rhoSol, uSol, PSol;
         int flag;
         if (Ps == MLH_PSTAR_VACUUM) {

@@ -1,7 +1,8 @@
 #!/bin/bash
-TAG=$1; shift
+# A/B of library builds on the scratch timings.  usage: bash tools/visit_ab.sh <tag> "<workloads>" lib1.so lib2.so ...
+TAG=$1; WL=$2; shift; shift
 OUT=gpurun_out; mkdir -p $OUT
-for so in libmlh_gpu.so "$@"; do
+for so in "$@"; do
   echo "=== $so"
-  MLH_GPU_LIB=$PWD/meshlesshydro_b200/$so timeout 300 python tools/quick_bench.py sedov61 kh1000j 2>&1 | grep -E "N=|k4b1|k4a|k4b3"
-done
+  MLH_GPU_LIB=$PWD/meshlesshydro_b200/$so timeout 400 python tools/quick_bench.py $WL 2>&1 | grep -E "N=|k[0-9]"
+done 2>&1 | tee $OUT/${TAG}_ab.log
