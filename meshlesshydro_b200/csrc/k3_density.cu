@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(128) k_density_matrix(const Params p) {
     {   // packed gather record for K3b / K4a
         double rec[MLH_PK1(D)];
 #pragma unroll
+        for (int k = 2 * D + 4; k < MLH_PK1(D); ++k) rec[k] = 0.; // padding (3D)
+#pragma unroll
         for (int k = 0; k < D; ++k) {
             rec[k] = xi[k];
             rec[D + k] = p.d.v[k][i];

@@ -888,27 +888,29 @@ __device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid
             MLH_ST_STAGE(pstar + fl, MLH_PSTAR_VACUUM);
         }
     }
-#pragma unroll
-    for (int kind = RS_NEWTON; kind <= RS_BRENT; ++kind) {
-        const bool mine = method == kind;
-        const unsigned m = __ballot_sync(0xffffffffu, mine);
-        if (!m) continue;
+    // one atomic instruction reserves the space of both kinds (lane 0: Newton starts, lane 1: Brent starts): the warp
+    // waits for ONE L2 round trip before its queue stores, not two (the wait was 19 % of the kernel's stall samples,
+    // profiles/r2t_k_face_setup_kh1000j_lines.txt)
+    const unsigned mN = __ballot_sync(0xffffffffu, method == RS_NEWTON), mB = __ballot_sync(0xffffffffu, method == RS_BRENT);
+    if (mN | mB) {
         const int region = (fl >> 5) % MLH_Q_REGIONS;
+        const int cnt = lane == 0 ? __popc(mN) : __popc(mB);
         int base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(qcount + 2 * region + (kind - RS_NEWTON), __popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (mine) {
-            int at = base + __popc(m & ((1u << lane) - 1u));
-            at = region * rcap + (kind == RS_BRENT ? rcap - 1 - at : at);
+        if (lane < 2 && cnt) base = atomicAdd(qcount + 2 * region + lane, cnt);
+        const int baseN = __shfl_sync(0xffffffffu, base, 0), baseB = __shfl_sync(0xffffffffu, base, 1);
+        if (method == RS_NEWTON || method == RS_BRENT) {
+            const bool brent = method == RS_BRENT;
+            int at = (brent ? baseB : baseN) + __popc((brent ? mB : mN) & ((1u << lane) - 1u));
+            at = region * rcap + (brent ? rcap - 1 - at : at);
             double *d = qd + at;
             const size_t qs = (size_t)MLH_Q_REGIONS * rcap; // field stride of the queue
             MLH_ST_STAGE(d + 0 * qs, q.rhoL); MLH_ST_STAGE(d + 1 * qs, q.PL); MLH_ST_STAGE(d + 2 * qs, q.aL);
             MLH_ST_STAGE(d + 3 * qs, q.rhoR); MLH_ST_STAGE(d + 4 * qs, q.PR); MLH_ST_STAGE(d + 5 * qs, q.aR);
             MLH_ST_STAGE(d + 6 * qs, q.du);
-            MLH_ST_STAGE(d + 7 * qs, kind == RS_NEWTON ? it.fa : it.a);
+            MLH_ST_STAGE(d + 7 * qs, brent ? it.a : it.fa);
             MLH_ST_STAGE(d + 8 * qs, it.b);
-            MLH_ST_STAGE(d + 9 * qs, kind == RS_NEWTON ? it.fb : it.fa);
-            MLH_ST_STAGE(d + 10 * qs, kind == RS_NEWTON ? it.c : it.fb);
+            MLH_ST_STAGE(d + 9 * qs, brent ? it.fa : it.fb);
+            MLH_ST_STAGE(d + 10 * qs, brent ? it.fb : it.c);
             MLH_ST_STAGE(d + 11 * qs, it.fpb);
             MLH_ST_STAGE(qi + at, fl);
         }
@@ -1214,9 +1216,10 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_fac
 #define MLH_SETUP_BLOCKS 8
 #endif
 #ifndef MLH_SETUP_PREFETCH
-// requesting the next trip's six fields before this trip computes LOST (A/B r2g, Sedov 61^3 / KH 1M: 0.131 -> 0.143 ms,
-// 1.259 -> 1.339 ms at 8 blocks/SM with spills; 0.129 / 1.327 at 6 blocks without): off
-#define MLH_SETUP_PREFETCH 0
+// 1: the six fields of the NEXT trip travel to shared memory (cp.async, no registers held) while this trip computes.
+// [Requesting them into registers LOST (A/B r2g, Sedov 61^3 / KH 1M: 0.131 -> 0.143 ms, 1.259 -> 1.339 ms at 8
+// blocks/SM with spills; 0.129 / 1.327 at 6 blocks without).]
+#define MLH_SETUP_PREFETCH 1
 #endif
 template <int D>
 __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_SETUP_BLOCKS) k_face_setup(const Params p, const double *__restrict__ stage, double *__restrict__ pstar,
@@ -1228,15 +1231,8 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_SETUP_BLOCKS) k_face_setup(
     const int nround = (f1 - f0 + 31) / 32 * 32; // whole warps stay in the loop (ballots in face_setup_and_queue)
     const int rcap = q_region_cap(cstride);
     using R = FaceRec<D>;
-    // (MLH_SETUP_PREFETCH: the six fields of the NEXT trip requested before this trip's ~600 instructions run)
     const int stride = gridDim.x * MLH_FACE_TILE;
     int fl = blockIdx.x * MLH_FACE_TILE + threadIdx.x;
-    double wn[6] = {1., 1., 0., 1., 1., 0.};
-    bool vn = fl < nround && f0 + fl < f1;
-    if (vn) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) wn[k] = stage[k * fs + fl];
-    }
 #if !MLH_SETUP_PREFETCH
     for (; fl < nround; fl += stride) { // (A/B variant: fields loaded when the trip starts)
         const bool valid = f0 + fl < f1;
@@ -1247,22 +1243,31 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_SETUP_BLOCKS) k_face_setup(
         }
         face_setup_and_queue(p, valid, fl, w[R::RHOL], w[R::PL], w[R::UL], w[R::RHOR], w[R::PR], w[R::UR], pstar, qd, qi, qcount, rcap);
     }
-    (void)vn;
-    (void)wn;
-    (void)stride;
 #else
+    // every thread copies and reads only its own slots: no block barrier, the thread's own wait_prior is enough
+    __shared__ double s_w[2][6][MLH_FACE_TILE];
+    int buf = 0;
+    if (fl < nround && f0 + fl < f1) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) __pipeline_memcpy_async(&s_w[0][k][threadIdx.x], stage + k * fs + fl, 8);
+    }
+    __pipeline_commit();
     for (; fl < nround; fl += stride) {
-        const bool valid = vn;
-        double w[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) w[k] = wn[k];
+        const bool valid = f0 + fl < f1;
         const int fnext = fl + stride;
-        vn = fnext < nround && f0 + fnext < f1;
-        if (vn) {
+        if (fnext < nround && f0 + fnext < f1) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) wn[k] = stage[k * fs + fnext];
+            for (int k = 0; k < 6; ++k) __pipeline_memcpy_async(&s_w[buf ^ 1][k][threadIdx.x], stage + k * fs + fnext, 8);
+        }
+        __pipeline_commit();
+        __pipeline_wait_prior(1); // this trip's group has landed; the next trip's stays in flight
+        double w[6] = {1., 1., 0., 1., 1., 0.};
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) w[k] = s_w[buf][k][threadIdx.x];
         }
         face_setup_and_queue(p, valid, fl, w[R::RHOL], w[R::PL], w[R::UL], w[R::RHOR], w[R::PR], w[R::UR], pstar, qd, qi, qcount, rcap);
+        buf ^= 1;
     }
 #endif
 }

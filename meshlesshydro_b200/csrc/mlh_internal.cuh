@@ -30,11 +30,20 @@
 #include "../../include/mlh_gpu.h"
 
 #define MLH_MAX_D 3
-#define MLH_PK1(D) (2 * (D) + 4)
+// 3D: 10 doubles.  [MLH_PK1_3D = 12 pads the record to 96 bytes = three 256-bit loads (load_packed) instead of five
+// 128-bit ones that straddle sectors: no gain (A/B r2q, Sedov 61^3 / 128^3: K3b 0.179 -> 0.178 / 1.531 -> 1.518 ms,
+// K4a 0.261 -> 0.263 / 2.386 -> 2.411); MLH_FREC_3D = 8 (64-byte flux records) LOST: update 0.087 -> 0.097 ms.]
+#ifndef MLH_PK1_3D
+#define MLH_PK1_3D 10
+#endif
+#define MLH_PK1(D) ((D) == 3 ? MLH_PK1_3D : 2 * (D) + 4)
 #define MLH_PK2(D) ((D) * (D) + ((D) + 2) * (D))
 #define MLH_NNL_IDX_BITS 26
 #define MLH_NNL_IDX_MASK ((1 << MLH_NNL_IDX_BITS) - 1)
-#define MLH_FREC(D) ((D) == 2 ? 4 : 6)      // doubles per face in the flux array (D+2 used)
+#ifndef MLH_FREC_3D
+#define MLH_FREC_3D 6
+#endif
+#define MLH_FREC(D) ((D) == 2 ? 4 : MLH_FREC_3D)      // doubles per face in the flux array (D+2 used)
 #define MLH_FMAP_SKIP 0xFFFFFFFCu           // slot without a face (partner's list overflowed)
 // K2 -> k_face_index word of an owned slot
 #define MLH_K2_OWNED 2u
@@ -195,12 +204,24 @@ __device__ __forceinline__ double q1_abs(double v, int mode) {
 }
 
 // 16-byte vector loads/stores of a packed record (PKn is even and the arrays are 256-byte aligned)
+// Packed records (pk1, pk2, F; bases 256-byte aligned by the carve).  A record of a multiple of four doubles is
+// 32-byte aligned and moves with 256-bit accesses (sm_100: LDG/STG.E.ENL2.256): one L1 sector look-up per 32 bytes
+// instead of two -- the gathers of K4a ran at 85 % of the L1 look-up rate (profiles/r2t_k_face_states_kh1000j_*).
+#ifndef MLH_WIDE_LDST
+#define MLH_WIDE_LDST 1
+#endif
 template <int N>
 __device__ __forceinline__ void load_packed(const double *__restrict__ src, double *dst) {
     static_assert(N % 2 == 0, "packed records hold an even number of doubles");
+    constexpr int NQ = (MLH_WIDE_LDST && N % 4 == 0) ? N / 4 : 0;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k)
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+            : "=d"(dst[4 * k]), "=d"(dst[4 * k + 1]), "=d"(dst[4 * k + 2]), "=d"(dst[4 * k + 3])
+            : "l"(src + 4 * k));
     const double2 *s2 = reinterpret_cast<const double2 *>(src);
 #pragma unroll
-    for (int k = 0; k < N / 2; ++k) {
+    for (int k = 2 * NQ; k < N / 2; ++k) {
         const double2 v = __ldg(s2 + k);
         dst[2 * k] = v.x;
         dst[2 * k + 1] = v.y;
@@ -209,9 +230,15 @@ __device__ __forceinline__ void load_packed(const double *__restrict__ src, doub
 template <int N>
 __device__ __forceinline__ void store_packed(double *dst, const double *src) {
     static_assert(N % 2 == 0, "packed records hold an even number of doubles");
+    constexpr int NQ = (MLH_WIDE_LDST && N % 4 == 0) ? N / 4 : 0;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k)
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
+                     :: "l"(dst + 4 * k), "d"(src[4 * k]), "d"(src[4 * k + 1]), "d"(src[4 * k + 2]), "d"(src[4 * k + 3])
+                     : "memory");
     double2 *d2 = reinterpret_cast<double2 *>(dst);
 #pragma unroll
-    for (int k = 0; k < N / 2; ++k) d2[k] = make_double2(src[2 * k], src[2 * k + 1]);
+    for (int k = 2 * NQ; k < N / 2; ++k) d2[k] = make_double2(src[2 * k], src[2 * k + 1]);
 }
 
 // displacement (neighbour - self) and distance for list entry e of particle i, the way the reference
