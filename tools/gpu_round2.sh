@@ -7,10 +7,11 @@ mkdir -p $OUT
 timeout 1200 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -5 > $OUT/${TAG}_gputests.log
 tail -3 $OUT/${TAG}_gputests.log
 M=smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__thread_inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
-for WL in sedov61 kh2000; do
-  B="python bench.py --workload $WL --steps 1 --warmup 3 --min-seconds 0 --no-cpu-baseline --no-e2e"
-  # the launches of 3 warm-up steps, the restart (+1 step) and the timed step come first; the profiled pass follows
-  timeout 900 ncu --clock-control none -k regex:'k_' -s 110 -c 40 --csv --log-file $OUT/${TAG}_ops_$WL.csv --metrics $M $B > $OUT/${TAG}_ncu_ops_$WL.log 2>&1
+for WL in sedov61 kh2000 kh1000; do
+  B="python bench.py --workload $WL --steps 5 --warmup 3 --min-seconds 0 --no-cpu-baseline --no-e2e"
+  # 3 warm-up steps and the restart (+1 step) come first (<= 100 launches); the window then covers timed steps, of which
+  # tools/ncu_ops.py takes the last complete one that does not follow an upload
+  timeout 900 ncu --clock-control none -k regex:'k_' -s 100 -c 90 --csv --log-file $OUT/${TAG}_ops_$WL.csv --metrics $M $B > $OUT/${TAG}_ncu_ops_$WL.log 2>&1
   python tools/ncu_ops.py $WL $OUT/${TAG}_ops_$WL.csv profiles/fp64_ops.json > $OUT/${TAG}_ops_$WL.txt; cat $OUT/${TAG}_ops_$WL.txt
 done
 cp profiles/fp64_ops.json $OUT/fp64_ops.json

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """ncu --csv metric dump (one launch per kernel) -> profiles/fp64_ops.json entry.
 usage: python tools/ncu_ops.py <workload> <ncu.csv> [profiles/fp64_ops.json]
-Per kernel of one step: FP64 thread operations (dfma, dmul, dadd), DRAM bytes, duration; the launch with the longest
-duration is kept for kernels that run more than once per step (chunk loop)."""
+Per kernel of one STEADY step (not the first step after an upload): FP64 thread operations (dfma, dmul, dadd), DRAM
+bytes, duration; the launch with the longest duration is kept for kernels that run more than once per step (chunk loop)."""
 import csv, json, os, sys
 NAMES = {"k_face_states": "k4a_face_states", "k_face_setup": "k4b1_face_setup", "k_face_iterate": "k4b_face_riemann",
          "k_face_finish": "k4b3_face_finish", "k_flux_sum_update": "k4c_flux_sum_update", "k_face_index": "k2b_face_index",
@@ -19,9 +19,30 @@ for r in rows[hdr + 1:]:
         continue
     d = dict(zip(h, r))
     launches.setdefault(d["ID"], {"name": d["Kernel Name"]})[d["Metric Name"]] = float(d["Metric Value"].replace(",", ""))
+# One STEADY step: the launch list is cut at every k_cell_key (first kernel of a step); segments that are incomplete
+# (no k_flux_sum_update), that contain an upload (k_iota) or that directly follow one (the first step from the initial
+# condition runs more Riemann iterations than the steps bench.py times) are dropped, the last remaining one is used.
+order = sorted(launches, key=lambda k: int(k))
+segs, cur = [], []
+for k in order:
+    if "k_cell_key" in launches[k]["name"] and cur:
+        segs.append(cur)
+        cur = []
+    cur.append(k)
+segs.append(cur)
+def has(seg, what):
+    return any(what in launches[k]["name"] for k in seg)
+good = [i for i, sg in enumerate(segs) if has(sg, "k_cell_key") and has(sg, "k_flux_sum_update") and not has(sg, "k_iota")
+        and not (i > 0 and has(segs[i - 1], "k_iota")) and i > 0]
+if not good:
+    sys.exit("ncu_ops.py: no steady step in the capture (%d segments)" % len(segs))
+step = segs[good[-1]]
+print("# %d launches captured, %d step segments, steady candidates %s, using segment %d (%d launches)"
+      % (len(order), len(segs), good, good[-1], len(step)))
 res = {}
-for L in launches.values():
-    short = next((v for k, v in NAMES.items() if k in L["name"]), None)
+for k in step:
+    L = launches[k]
+    short = next((v for kk, v in NAMES.items() if kk in L["name"]), None)
     if not short:
         continue
     e = {"dfma": L.get("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", 0.0),
