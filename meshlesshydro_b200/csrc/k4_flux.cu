@@ -951,6 +951,9 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_fac
     // while this trip computes: a block's 128 consecutive faces belong to ~8 neighbouring owners that share most of
     // their partners, ~50 distinct records (11 KB) per trip -- the kernel was waiting on exactly those first-touch
     // misses (long-scoreboard 5.9 of 10 stalled warps at 25 % occupancy, profiles/r01s).
+    // [Copying the four records of the next trip to shared memory with cp.async (16-byte chunks, own slots, no barrier)
+    // instead LOST by 2.4-2.7x (A/B r3c: 0.26 -> 0.62 ms at 61^3, 3.07 -> 8.39 ms at KH 4M): 20-34 scattered 16-byte
+    // copies per thread cost more LSU issue than the 256-bit gathers they replace and take 40-70 KB of L1 per block.]
     const int stride = gridDim.x * MLH_FACE_TILE;
     int fl = blockIdx.x * MLH_FACE_TILE + threadIdx.x;
     int fav_next = 0, e_next = 0;
