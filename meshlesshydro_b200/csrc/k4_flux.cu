@@ -932,6 +932,12 @@ __device__ __forceinline__ void face_setup_and_queue(const Params &p, bool valid
 #ifndef MLH_FUSE_SETUP
 #define MLH_FUSE_SETUP 0
 #endif
+// L1 prefetch of the next trip's gather records: still a gain in 3D (0.273 -> 0.261 ms at 61^3), but since the records
+// move with 256-bit loads it LOSES in 2D, where the kernel is bound by L1 look-ups and every prefetch is one more
+// (A/B r3d, KH 1M / 4M: 0.764 -> 0.659, 3.05 -> 2.68 ms without it)
+#ifndef MLH_K4A_PREFETCH
+#define MLH_K4A_PREFETCH(D) ((D) == 3)
+#endif
 // FUSE (off): the solver setup (k_face_setup's body) runs on the states while they are still in registers, so the staged
 // record is read once instead of twice.  Measured (A/B, profiles/README.md r01q): no gain at Sedov 61^3 (0.561 ms vs
 // 0.370 + 0.188 ms) and a loss at KH 1M (2.52 vs 0.98 + 1.36 ms) -- 3x the spills and a 75 KB instruction footprint.
@@ -1043,7 +1049,7 @@ __global__ void __launch_bounds__(MLH_FACE_TILE, MLH_K4A_BLOCKS_PER_SM(D)) k_fac
                 }
         }
 
-        if (valid_next) { // the list entries of the next trip have arrived by now; start its record fetches
+        if (MLH_K4A_PREFETCH(D) && valid_next) { // the list entries of the next trip have arrived by now; start its record fetches
             const int in = fav_next & 0x7FFFFFFF, jn = e_next & MLH_NNL_IDX_MASK;
             const char *r1i = (const char *)(p.d.pk1 + (size_t)in * PK1), *r1j = (const char *)(p.d.pk1 + (size_t)jn * PK1);
             const char *r2i = (const char *)(p.d.pk2 + (size_t)in * PK2), *r2j = (const char *)(p.d.pk2 + (size_t)jn * PK2);
