@@ -743,7 +743,9 @@ __device__ __forceinline__ void face_store(double *rec, size_t fs, const double 
 // member mask, list length and face base of its partner -- five dependent gathers, 0.10 ms at 61^3,
 // profiles/r02_k_face_index_ncu_full.txt; a search of the partner's list cost 0.27-0.42 ms, profiles/r01h.]
 // Periodic-image slots (few) and cells of more than 32 particles find the partner's slot by scanning its list.
+#ifndef MLH_FI_STAGE
 #define MLH_FI_STAGE 4096 // faces staged per block (32 KB): 128 particles x ~16 (3D) .. ~24 (2D) owned slots
+#endif
 template <bool PER>
 __global__ void __launch_bounds__(128) k_face_index(const Params p) {
     // The faces of a block's 128 consecutive particles are one contiguous range of the face list: (owner, entry) pairs
