@@ -29,7 +29,7 @@ template <int D, bool PER>
 __device__ __forceinline__ void load_neighbour(const Params &p, int e, double *nb) {
     const int j = e & MLH_NNL_IDX_MASK;
     load_packed<MLH_PK1(D)>(p.d.pk1 + (size_t)j * MLH_PK1(D), nb);
-    if (PER) {
+    if (PER && ((unsigned)e >> MLH_NNL_IDX_BITS) != 0u) { // image entries only (10 % of the kernel's instructions when unconditional)
 #pragma unroll
         for (int k = 0; k < D; ++k) nb[k] = image_coord(nb[k], (e >> (MLH_NNL_IDX_BITS + 2 * k)) & 3, p.grid.bmin[k], p.grid.bmax[k]);
     }

@@ -250,7 +250,7 @@ __device__ __forceinline__ void neighbour_geometry(const Params &p, const double
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         double xj = p.d.x[k][j]; // SoA on purpose: the neighbours of one stencil cell are consecutive j, i.e. 4 per sector
-        if (PER) {
+        if (PER && ((unsigned)e >> MLH_NNL_IDX_BITS) != 0u) { // few entries are images: the branch is warp-uniform almost always
             int ck = (e >> (MLH_NNL_IDX_BITS + 2 * k)) & 3;
             xj = image_coord(xj, ck, p.grid.bmin[k], p.grid.bmax[k]);
         }
@@ -274,7 +274,7 @@ __device__ __forceinline__ void neighbour_geometry_from(const Params &p, const d
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         double xj = xjraw[k];
-        if (PER) {
+        if (PER && ((unsigned)e >> MLH_NNL_IDX_BITS) != 0u) { // few entries are images: the branch is warp-uniform almost always
             int ck = (e >> (MLH_NNL_IDX_BITS + 2 * k)) & 3;
             xj = image_coord(xj, ck, p.grid.bmin[k], p.grid.bmax[k]);
         }
