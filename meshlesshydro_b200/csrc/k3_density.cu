@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(128) k_density_matrix(const Params p) {
         store_packed<MLH_PK1(D)>(p.d.pk1 + (size_t)i * MLH_PK1(D), rec);
     }
     // E matrix
+    const double inv_omg = __ddiv_rn(1., omg);
     double E[D * D];
 #pragma unroll
     for (int k = 0; k < D * D; ++k) E[k] = 0.;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(128) k_density_matrix(const Params p) {
         if (s + 2 < ntot) e_next2 = p.d.nnl[(size_t)(s + 2) * p.ncap + i];
         if (s + 1 < ntot) neighbour_position<D>(p, e_next, xn);
         neighbour_geometry_from<D, PER>(p, xi, e, xc, d, &r);
-        double psij = __ddiv_rn(cubic_spline(r, p), omg);
+        double psij = mlh_div_known(cubic_spline(r, p), omg, inv_omg);
 #pragma unroll
         for (int a = 0; a < D; ++a)
 #pragma unroll

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(128, MLH_K3B_BLOCKS(D)) k_gradient_limit(const
 #pragma unroll
         for (int k = 0; k < D * D; ++k) B[k] = p.d.B[k][i];
         const double omg = own[2 * D + 3];
+        const double inv_omg = __ddiv_rn(1., omg);
         const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
 
         double g[NF][D];
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(128, MLH_K3B_BLOCKS(D)) k_gradient_limit(const
                 sd[k] = __dsub_rn(xi[k], nb[k]);
             }
             const double r = sqrt(dist_sqr_exact<D>(sd)); // Particles.cpp:1170-1175 / :2275-2280
-            const double psij = __ddiv_rn(cubic_spline(r, p), omg);
+            const double psij = mlh_div_known(cubic_spline(r, p), omg, inv_omg);
             double pt[D];
 #pragma unroll
             for (int a = 0; a < D; ++a) {

@@ -353,6 +353,7 @@ int mlh_create(const mlh_config *cfg, mlh_ctx **out) {
     {   // Kernel::cubicSpline constants, Particles.cpp:10-15
         double h2 = p.h / 2.;
         p.h2 = h2;
+        p.inv_h2 = 1. / h2; // correctly rounded on the host
         p.sigma = (p.D == 2) ? 10. / (7. * M_PI * h2 * h2) : 1. / (M_PI * h2 * h2 * h2);
         p.sigma4 = p.sigma / 4.;
     }
