@@ -743,6 +743,9 @@ __device__ __forceinline__ void face_store(double *rec, size_t fs, const double 
 // member mask, list length and face base of its partner -- five dependent gathers, 0.10 ms at 61^3,
 // profiles/r02_k_face_index_ncu_full.txt; a search of the partner's list cost 0.27-0.42 ms, profiles/r01h.]
 // Periodic-image slots (few) and cells of more than 32 particles find the partner's slot by scanning its list.
+#ifndef MLH_FI_TRIP
+#define MLH_FI_TRIP 8 // list slots per trip (their loads and gathers are independent; 8 vs 4: 1.62 -> 1.58 ms at KH 4M, r3k)
+#endif
 #ifndef MLH_FI_STAGE
 #define MLH_FI_STAGE 4096 // faces staged per block (32 KB): 128 particles x ~16 (3D) .. ~24 (2D) owned slots
 #endif
@@ -761,24 +764,24 @@ __global__ void __launch_bounds__(128) k_face_index(const Params p) {
     if (i < p.own_end) {
     const int nreg = p.d.noi[i], ntot = nreg + p.d.noig[i];
     const int fs = p.d.face_start[i];
-    for (int s0 = 0; s0 < ntot; s0 += 4) {
-        unsigned v[4], g0[4];
-        int e[4];
+    for (int s0 = 0; s0 < ntot; s0 += MLH_FI_TRIP) {
+        unsigned v[MLH_FI_TRIP], g0[MLH_FI_TRIP];
+        int e[MLH_FI_TRIP];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < MLH_FI_TRIP; ++q) {
             const int s = s0 + q < ntot ? s0 + q : ntot - 1;
             const size_t at = (size_t)s * p.ncap + i;
             v[q] = p.d.fmap[at];
             e[q] = p.d.nnl[at];
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { // the four gathers of a trip are independent
+        for (int q = 0; q < MLH_FI_TRIP; ++q) { // the four gathers of a trip are independent
             g0[q] = 0u;
             if ((v[q] & MLH_K2_OWNED) && !(v[q] & (MLH_K2_NOPARTNER | MLH_K2_GHOST)))
                 g0[q] = p.d.grp[(size_t)((v[q] >> MLH_K2_SC_SHIFT) & 31u) * p.ncap + (e[q] & MLH_NNL_IDX_MASK)];
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < MLH_FI_TRIP; ++q) {
             const int s = s0 + q;
             if (s >= ntot) break;
             if (!(v[q] & MLH_K2_OWNED)) continue; // the partner owns the pair: it fills this slot
