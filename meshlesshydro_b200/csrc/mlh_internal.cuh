@@ -166,7 +166,7 @@ __device__ __forceinline__ double cube_cr(double t) {
 // faithful approximation, and Markstein's theorem (Handbook of Floating-Point Arithmetic, section 4.7: y = RN(1/b), q
 // faithful, r = a - b q exact by FMA  =>  RN(q + r y) = RN(a/b)) makes the second step exact.  Operands here are far
 // from the overflow / underflow ranges the theorem excludes; zero, infinity and NaN behave as in a division.
-// oracle-side check: 7e8 random quotients incl. the h/2 values of all test cases, 0 mismatches against a / b.
+// CPU check of the same sequence against a / b: tests/test_div_known.py (12 M quotients per run; 7e8 once, 0 mismatches).
 __device__ __forceinline__ double mlh_div_known(double a, double b, double y) {
     double q = __dmul_rn(a, y);
     q = __fma_rn(__fma_rn(-b, q, a), y, q);
