@@ -93,8 +93,12 @@ class SedovTaylor:
         k2 = k6 / g
         k3 = (n * g - n + 2.0) / (w1 * k6)
         k4 = (n + 2.0) * a0 * k6
-        f = np.logspace(np.log10(k2), 0.0, int(samples))[1:]  # from the centre (f -> k2) to the shock (f = 1)
-        A, B, C = k1 * (f - k2), k3 * (k4 - f), k5 * (k6 - f)
+        # from the centre (f -> k2, where r/R_s ~ (f - k2)^a2 with a2 ~ 0.1) to the shock (f = 1): the distance from k2
+        # is sampled logarithmically down to 1e-60, i.e. r/R_s < 1e-3 -- sampling f itself left the inner quarter of
+        # the radius, where the pressure stays finite, out of the energy integral (xi0 0.24 % too large)
+        delta = np.logspace(-60.0, np.log10(1.0 - k2), int(samples))
+        f = k2 + delta
+        A, B, C = k1 * delta, k3 * (k4 - f), k5 * (k6 - f)
         eta = f ** (-a6) * A ** a2 * B ** (-a1)          # r / R_s
         dens = A ** a3 * B ** a4 * C ** (-a5)            # rho / rho_shock
         pres = f ** a8 * B ** (a4 - 2.0 * a1) * C ** (1.0 - a5)  # P / P_shock
