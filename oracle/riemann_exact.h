@@ -16,6 +16,9 @@
  * two-shock initial guess, Brent fallback, sampling at x/t = dxdt) and is THE
  * definition the oracle, the reference-source build (oracle/_ref) and the CUDA
  * kernels are all held to.  The reference has no test or golden vector for it.
+ * What IS pinned (tests/test_riemann_kat.py): the SOLUTION -- Toro's tables 4.1-4.3 to five digits, and an
+ * independent 40-digit restatement of the exact solution (mpmath, from the book) on 1500 random states to <= 1e-10
+ * (measured 1.5e-12).  What stays unpinned: the third-party code's iteration path inside its 5e-9 stopping rule.
  *
  * Plain C99 (also valid C++), header-only.
  */
