@@ -19,19 +19,22 @@
 // evaluate a cut face redundantly with identical operands, so conservation holds across slabs without a flux exchange.
 //
 // Kernels:
-//   k_face_index      thread per particle, four list slots per trip: face list fa/fe (owner + canonical bit, list
-//                     entry) and the slot -> face map (fmap); a partner-owned slot is located in the partner's list
-//                     from the group start + bit mask K2 recorded (no search).
+//   k_face_index      thread per particle, MLH_FI_TRIP list slots per trip, OWNERS only: face list fa/fe (owner +
+//                     canonical bit, list entry; staged in shared memory, written as full lines) and the slot -> face
+//                     map (fmap); the owner scatters the face index into the partner's slot, which it finds from the
+//                     group start (grp) + the offset r K2 recorded (no search).
 //   k_face_states (K4a)  thread per face (persistent grid, two waves): A_ij, boosted + reconstructed + limited +
-//                        predicted states of both endpoints -> face record (4D+4 doubles) in a field-major staging
-//                        buffer.  Gather/latency-bound; consecutive faces share their owner (warp broadcast), the face
-//                        list is read one trip ahead and the next trip's records are prefetched into L1.
-//   k_face_setup / k_face_iterate / k_face_finish (K4b)  the Riemann class of the reference: rotate into the face
-//                        frame + start of the exact solver (faces that need iterations go to a queue) / persistent
-//                        lanes iterate queued faces to convergence (Newton-Raphson, Brent), state in registers, warp-
-//                        private cp.async rings / star state at x/t = 0, rotation back, projection -> F (D+2 doubles,
-//                        canonical orientation).  setup and finish stream at 60-80 % of the HBM peak, the iteration
-//                        is a dependent FP64 chain per lane.
+//                        predicted states of both endpoints, rotated into the face frame -> face record (4D+4 doubles)
+//                        in a field-major staging buffer.  Gather/latency-bound; consecutive faces share their owner
+//                        (warp broadcast), the face list is read one trip ahead, the records move with 256-bit loads
+//                        (3D also prefetches the next trip's records into L1).
+//   k_face_setup / k_face_iterate / k_face_finish (K4b)  the Riemann class of the reference: start of the exact
+//                        solver on the six normal-direction fields (faces that need iterations go to a queue; faces
+//                        whose guess already is the root are finished) / persistent lanes iterate queued faces to
+//                        convergence (Newton-Raphson, Brent with the early exit of DESIGN.md 3.2), state in registers,
+//                        warp-private cp.async rings / star state at x/t = 0, rotation back, projection -> F (D+2
+//                        doubles, canonical orientation).  setup and finish stream at 55-80 % of the HBM peak, the
+//                        iteration is a dependent FP64 chain per lane.
 //                        [The first version fused everything into one 255-register, 145 KB kernel: ncu showed 56 %
 //                        of the warp stalls were instruction fetches and 14 % FP64-pipe use -- profiles/r01a_*.]
 //   k_flux_sum_update (K4c/K5) thread per particle, four slots per trip: signed sum of the faces of its slots in list
@@ -1643,7 +1646,7 @@ int mlh_launch_face_index(mlh_ctx *c) {
     return MLH_OK;
 }
 
-// staging buffer per face of one chunk: record (4D+4 doubles), P*, solver queue (11 doubles + 1 int)
+// staging buffer per face of one chunk: record (4D+4 doubles), P*, solver queue (MLH_Q_FIELDS = 12 doubles + 1 int)
 int mlh_stage_alloc(mlh_ctx *c) {
     Params &p = c->p;
     const size_t per_face = (size_t)(4 * p.D + 4 + 1 + MLH_Q_FIELDS) * sizeof(double) + sizeof(int);
