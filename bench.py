@@ -164,7 +164,8 @@ def time_reference(ic_factory, preset, n_side, steps, warmup, budget_s):
 # ------------------------------------------------------------------------------------------------
 SIDES = {"sedov61": 61, "sedov128": 128, "sedov256": 256, "kh100": 100, "kh1000": 1000, "kh2000": 2000, "fb1000": 1000}
 BLOCK_CAP = {"fb1000": 5}  # steps per timed block (see run_workload)
-CPU_SIDES = {"sedov61": 61, "sedov128": 61, "sedov256": 61, "kh100": 100, "kh1000": 200, "kh2000": 200, "fb1000": 200}
+# cpu_baseline sample: 10-30 s of single-core work (time_reference shrinks the side to fit its 25 s budget)
+CPU_SIDES = {"sedov61": 61, "sedov128": 61, "sedov256": 61, "kh100": 100, "kh1000": 400, "kh2000": 400, "fb1000": 400}
 
 
 def mgpu_bitwise_check(dist, local_rank, rank, world):
