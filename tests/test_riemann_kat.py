@@ -77,7 +77,16 @@ def test_vacuum_generation(solve):
 # the solver's P* is guaranteed only to ~1e-8 relative -- in practice Newton/Brent land within 2e-12, and the bound
 # asserted below is 1e-10, the bar of the GPU parity tests).  Toro's tables pin five digits of five problems; this
 # pins ten digits of 1500 random ones (density / pressure ratios up to 1e8), both gammas of the shipped cases.
-def _exact_at_origin(g, rhoL, uL, PL, rhoR, uR, PR):
+def _exact_at_origin(g, rhoL, uL, PL, rhoR, uR, PR, with_side=False):
+    """(rho, u, P) at x/t = 0, or None if vacuum is generated; with_side: a 4th value, True if the point lies left of
+    the contact (the transverse velocities of that side are advected through the face, Riemann.cpp:104-127)"""
+    res = _exact_at_origin_impl(g, rhoL, uL, PL, rhoR, uR, PR)
+    if res is None or with_side:
+        return res
+    return res[:3]
+
+
+def _exact_at_origin_impl(g, rhoL, uL, PL, rhoR, uR, PR):
     import mpmath as mp
     mp.mp.dps = 40
     g, rhoL, uL, PL, rhoR, uR, PR = [mp.mpf(float(v)) for v in (g, rhoL, uL, PL, rhoR, uR, PR)]
@@ -102,25 +111,25 @@ def _exact_at_origin(g, rhoL, uL, PL, rhoR, uR, PR):
         if ps > PL:
             SL = uL - aL * mp.sqrt((g + 1) / (2 * g) * ps / PL + gp)
             if SL >= 0:
-                return rhoL, uL, PL
-            return rhoL * (ps / PL + gm) / (gm * ps / PL + 1), us, ps
+                return rhoL, uL, PL, True
+            return rhoL * (ps / PL + gm) / (gm * ps / PL + 1), us, ps, True
         if uL - aL >= 0:
-            return rhoL, uL, PL
+            return rhoL, uL, PL, True
         if us - aL * (ps / PL) ** gp < 0:
-            return rhoL * (ps / PL) ** (1 / g), us, ps
+            return rhoL * (ps / PL) ** (1 / g), us, ps, True
         c = 2 / (g + 1) + gm / aL * uL  # inside the left fan at S = 0
-        return rhoL * c ** (2 / (g - 1)), 2 / (g + 1) * (aL + (g - 1) / 2 * uL), PL * c ** (2 * g / (g - 1))
+        return rhoL * c ** (2 / (g - 1)), 2 / (g + 1) * (aL + (g - 1) / 2 * uL), PL * c ** (2 * g / (g - 1)), True
     if ps > PR:
         SR = uR + aR * mp.sqrt((g + 1) / (2 * g) * ps / PR + gp)
         if SR <= 0:
-            return rhoR, uR, PR
-        return rhoR * (ps / PR + gm) / (gm * ps / PR + 1), us, ps
+            return rhoR, uR, PR, False
+        return rhoR * (ps / PR + gm) / (gm * ps / PR + 1), us, ps, False
     if uR + aR <= 0:
-        return rhoR, uR, PR
+        return rhoR, uR, PR, False
     if us + aR * (ps / PR) ** gp > 0:
-        return rhoR * (ps / PR) ** (1 / g), us, ps
+        return rhoR * (ps / PR) ** (1 / g), us, ps, False
     c = 2 / (g + 1) - gm / aR * uR
-    return rhoR * c ** (2 / (g - 1)), 2 / (g + 1) * (-aR + (g - 1) / 2 * uR), PR * c ** (2 * g / (g - 1))
+    return rhoR * c ** (2 / (g - 1)), 2 / (g + 1) * (-aR + (g - 1) / 2 * uR), PR * c ** (2 * g / (g - 1)), False
 
 
 @pytest.mark.parametrize("gamma", [1.4, 5.0 / 3.0])
